@@ -1,0 +1,120 @@
+"""Pin the oracle (oracle/ref_fft.cpp) to the reference's own golden vectors.
+
+Mirrors fft/tests.mojo: `_test_fft` (:274-371) x forward/inverse, `test_2d_cpu`
+(:461-518), `test_3d_cpu` (:908-970), at the reference's atol=1e-2 / rtol=1e-5
+(:40-41). The goldens are printed to 3 decimals, so the bound here is 2e-3.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+with open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")) as f:
+    _G = json.load(f)
+CASES = [(c["length"], tuple(c["bases"])) for c in _G["cases_1d"]]
+
+
+def c2(a):
+    return a[..., 0] + 1j * a[..., 1]
+
+
+def test_golden_fixture_is_complete(golden):
+    assert sum(len(v) for v in golden["vectors_1d"].values()) == 65
+    assert len(golden["cases_1d"]) == 56
+    assert golden["nd"]["2d"]["dims"] == [6, 4] and golden["nd"]["3d"]["dims"] == [6, 4, 8]
+
+
+@pytest.mark.parametrize("length,bases", CASES)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_1d_forward_golden(oracle, golden, length, bases, dtype):
+    vs = golden["vectors_1d"][str(length)]
+    x = np.array([v["x"] for v in vs], dtype=dtype)[:, :, None]  # (B, N, 1): real input
+    want = np.array([v["X"] for v in vs], dtype=np.float64)
+    got = oracle.ref_fft(x, bases=[list(bases)], out_dtype=dtype)
+    np.testing.assert_allclose(got, want, atol=golden["atol"], rtol=golden["rtol"])
+    assert np.abs(got - want).max() < 2e-3
+
+
+@pytest.mark.parametrize("length,bases", CASES)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_1d_inverse_golden(oracle, golden, length, bases, dtype):
+    vs = golden["vectors_1d"][str(length)]
+    spec = np.array([v["X"] for v in vs], dtype=dtype)  # (B, N, 2)
+    want = np.array([v["x"] for v in vs], dtype=np.float64)
+    got = oracle.ref_fft(spec, bases=[list(bases)], inverse=True, out_dtype=dtype)
+    np.testing.assert_allclose(got[..., 0], want, atol=golden["atol"], rtol=golden["rtol"])
+    np.testing.assert_allclose(got[..., 1], 0, atol=golden["atol"])
+
+
+@pytest.mark.parametrize("key", ["2d", "3d"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_nd_golden_uint8_input(oracle, golden, key, dtype):
+    d = golden["nd"][key]
+    x = np.array(d["x"], dtype=np.uint8).reshape([1] + d["dims"] + [1])
+    want = np.array(d["X"], dtype=np.float64).reshape([1] + d["dims"] + [2])
+    got = oracle.ref_fft(x, out_dtype=dtype)
+    np.testing.assert_allclose(got, want, atol=golden["atol"], rtol=golden["rtol"])
+
+
+def test_ordered_bases_rules(oracle):
+    # _utils.mojo:163-221 examples
+    assert oracle.ordered_bases(8, [2]) == [2, 2, 2]
+    assert oracle.ordered_bases(16, [2, 4]) == [4, 4]
+    assert oracle.ordered_bases(20, [5, 2]) == [5, 2, 2]
+    assert oracle.ordered_bases(48, [3, 2]) == [3, 2, 2, 2, 2]
+    assert oracle.ordered_bases(60, [5, 3, 2]) == [5, 3, 2, 2]
+    assert oracle.ordered_bases(60, [6, 5, 2]) == [6, 5, 2]
+    assert oracle.ordered_bases(60, [3, 4, 5]) == [5, 4, 3]
+    assert oracle.ordered_bases(93, [3, 31]) == [31, 3]
+    assert oracle.ordered_bases(60, [7, 2]) is None     # product never reaches 60
+    assert oracle.ordered_bases(8, [1, 2]) is None      # base 1 rejected
+
+
+def test_default_bases(oracle):
+    # fft.mojo:49-104
+    assert oracle.default_bases(128, "gpu") == [2] * 7
+    assert oracle.default_bases(93, "gpu") == [31, 3]
+    assert oracle.default_bases(480, "gpu") == [5, 3, 2, 2, 2, 2, 2]
+    assert oracle.default_bases(640, "gpu") == [5] + [2] * 7
+    assert sorted(oracle.default_bases(93, "cpu")) == [3, 31]
+    assert oracle.default_bases(97 * 2, "cpu") == [2, 97]
+
+
+SHAPES = [(3, 1024), (4, 93), (5, 128), (2, 48, 40), (2, 16, 16, 16), (1, 6, 10, 12, 14), (2, 97), (1, 194)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("inverse", [False, True])
+def test_random_vs_numpy(oracle, shape, inverse):
+    """numpy float64 fftn is the independent second oracle."""
+    rng = np.random.default_rng(hash(shape) % 2**32)
+    x = rng.standard_normal(shape + (2,)).astype(np.float32)
+    axes = tuple(range(1, len(shape)))
+    xc = c2(x.astype(np.float64))
+    want = np.fft.ifftn(xc, axes=axes) if inverse else np.fft.fftn(xc, axes=axes)
+    got32 = c2(oracle.ref_fft(x, inverse=inverse).astype(np.float64))
+    got64 = c2(oracle.ref_fft(x, inverse=inverse, out_dtype=np.float64))
+    assert np.linalg.norm(got64 - want) / np.linalg.norm(want) < 1e-13
+    # stated fp32 tolerance of the reference arithmetic (fp32 theta twiddles)
+    assert np.linalg.norm(got32 - want) / np.linalg.norm(want) < 5e-6
+    assert np.abs(got32 - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_real_input_full_spectrum(oracle):
+    """in_layout (..., 1): stage 0 reads reals, output is the FULL spectrum (_fft.mojo:254-255)."""
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((3, 20, 12, 1)).astype(np.float32)
+    want = np.fft.fftn(x[..., 0].astype(np.float64), axes=(1, 2))
+    got = c2(oracle.ref_fft(x, out_dtype=np.float64))
+    assert got.shape == want.shape
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+
+
+def test_workers_do_not_change_result(oracle):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((6, 24, 20, 2)).astype(np.float32)
+    a = oracle.ref_fft(x, workers=1)
+    b = oracle.ref_fft(x, workers=4)
+    assert np.array_equal(a, b)
