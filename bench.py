@@ -1,0 +1,424 @@
+#!/usr/bin/env python3
+"""bench.py — the driver's measurement contract for the batched N-d radix-n FFT hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-shapes]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one forward C2C transform of the primary workload (BASELINE.json configs[1]:
+1-D C2C fp32, batch 100000 x 1024) through the C ABI (b200fft_exec). At N > 1 every rank
+owns its own batch of that shape (batch sharding, no data-path collective, "weak"
+scaling); the time is the max over ranks and `value` the whole-job GFLOP/s
+(5*N*log2(N) per transform, the north-star's effective-flop model).
+
+Printed on rank 0: ONE JSON line with value / ms_per_step, `roofline` (HBM, measured
+peak from MEASURED_PEAKS.json), `cpu_baseline` (the oracle = C++ port of the
+reference's CPU path, timed on the box's host cores), `e2e` (same metric through
+b200fft_exec_host with pinned HOST buffers, copies inside the timed region),
+`gpu_launches`, `clocks`, and `shapes`: every BASELINE.json single-GPU config timed
+the same way next to cuFFT (same buffers, same stream, CUDA events).
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle
+port; the Mojo original cannot run in this image) with all host threads.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "hackathon-fft_b200", "python")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+METRIC = "batched C2C FFT ms, GFLOP/s & HBM GB/s vs peak at 1/2/4/8 B200 vs cuFFT"
+PRIMARY = {"name": "1D C2C fp32 100000x1024", "shape": (100000, 1024)}
+# BASELINE.json single-GPU configs (shape = (batch, dims...)); r2c = real input
+SHAPES = [
+    ("1d_500000x128", (500000, 128), False),
+    ("1d_100000x1024", (100000, 1024), False),
+    ("1d_500000x93", (500000, 93), False),
+    ("2d_100x640x480", (100, 640, 480), False),
+    ("2d_100x640x480_r2c_full", (100, 640, 480), True),
+    ("3d_100x64x64x64", (100, 64, 64, 64), False),
+    ("3d_10x128x128x128", (10, 128, 128, 128), False),
+    ("3d_1x256x256x256", (1, 256, 256, 256), False),
+    ("3d_1x512x512x512", (1, 512, 512, 512), False),
+]
+
+
+def flops_c2c(shape):
+    n = int(np.prod(shape[1:]))
+    return 5.0 * n * math.log2(n) * shape[0]
+
+
+def algorithmic_bytes(shape, real_in=False):
+    pts = int(np.prod(shape))
+    return pts * (4 if real_in else 8) + pts * 8
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+            return self
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def physical_gpu_index(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:
+            return local_index
+    return local_index
+
+
+class CuFFT:
+    """cuFFT through baseline/libcufft_shim.so (same call as the reference's cufft_benchmark.cu)."""
+
+    def __init__(self, shape, r2c=False):
+        path = os.path.join(ROOT, "baseline", "libcufft_shim.so")
+        self.lib = ctypes.CDLL(path)
+        self.lib.cufft_shim_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                               ctypes.POINTER(ctypes.c_longlong), ctypes.c_longlong, ctypes.c_int,
+                                               ctypes.POINTER(ctypes.c_size_t)]
+        self.lib.cufft_shim_exec.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int]
+        self.lib.cufft_shim_destroy.argtypes = [ctypes.c_void_p]
+        dims = (ctypes.c_longlong * (len(shape) - 1))(*shape[1:])
+        self.h = ctypes.c_void_p()
+        ws = ctypes.c_size_t()
+        rc = self.lib.cufft_shim_create(ctypes.byref(self.h), len(shape) - 1, dims, shape[0], int(r2c), ctypes.byref(ws))
+        if rc:
+            raise RuntimeError("cufft plan failed: %d" % rc)
+        self.r2c, self.work = r2c, ws.value
+
+    def exec(self, x, out, stream):
+        rc = self.lib.cufft_shim_exec(self.h, x.data_ptr(), out.data_ptr(), stream, int(self.r2c), 0)
+        if rc:
+            raise RuntimeError("cufft exec failed: %d" % rc)
+
+    def destroy(self):
+        self.lib.cufft_shim_destroy(self.h)
+
+
+def time_gpu(fn, warmup, steps, torch):
+    """CUDA-event timing on the current stream (the stream the kernels are launched on)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def cpu_reference_time(shape, real_in, workers, budget_s=12.0, repeats=2):
+    """Time the oracle (C++ port of the reference CPU path, workers=n) on a bounded sample
+    of the workload's batch; returns (ms for the FULL batch extrapolated linearly, sample batch, threads)."""
+    import oracle
+    threads = workers or oracle.hardware_threads()
+    per = int(np.prod(shape[1:]))
+    # size the sample from a quick probe
+    probe_b = max(1, min(shape[0], max(threads, 200000 // per)))
+    rng = np.random.default_rng(0)
+    comps = 1 if real_in else 2
+    x = rng.standard_normal((probe_b,) + tuple(shape[1:]) + (comps,)).astype(np.float32)
+    t0 = time.perf_counter()
+    oracle.ref_fft(x, workers=threads)
+    t_probe = time.perf_counter() - t0
+    sample_b = int(max(1, min(shape[0], probe_b * (budget_s / repeats) / max(t_probe, 1e-4))))
+    if sample_b != probe_b:
+        x = rng.standard_normal((sample_b,) + tuple(shape[1:]) + (comps,)).astype(np.float32)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        oracle.ref_fft(x, workers=threads)
+        best = min(best, time.perf_counter() - t0)
+    return best * 1e3 * shape[0] / sample_b, sample_b, threads
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port, all
+    host threads) on the same config / metric / unit. Rank 0 only under torchrun."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+    oracle.build()
+    shape = PRIMARY["shape"]
+    threads = oracle.hardware_threads()
+    per = int(np.prod(shape[1:]))
+    # one step = a bounded sample of the workload: scale the batch so K+W steps end in minutes
+    rng = np.random.default_rng(0)
+    probe = rng.standard_normal((max(threads, 64),) + tuple(shape[1:]) + (2,)).astype(np.float32)
+    t0 = time.perf_counter()
+    oracle.ref_fft(probe, workers=threads)
+    t_probe = time.perf_counter() - t0
+    total_steps = max(1, args.steps + args.warmup)
+    target_s = min(20.0, 120.0 / total_steps)
+    sample_b = int(max(1, min(shape[0], probe.shape[0] * target_s / max(t_probe, 1e-4))))
+    x = rng.standard_normal((sample_b,) + tuple(shape[1:]) + (2,)).astype(np.float32)
+    for _ in range(args.warmup):
+        oracle.ref_fft(x, workers=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.ref_fft(x, workers=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    gflops = flops_c2c((sample_b,) + tuple(shape[1:])) / dt / 1e9
+    ms_full = dt * 1e3 * shape[0] / sample_b
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": PRIMARY["name"], "note": "CPU reference path (workers=n): C++ port of the Mojo "
+                   "radix-n implementation (oracle/ref_fft.cpp); ms_per_step extrapolated to the full batch"},
+        "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+                         "sample": "%d of %d transforms of length %d per step" % (sample_b, shape[0], per)},
+        "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def bench_shape(name, shape, real_in, torch, b200fft, steps, warmup, peak):
+    """ours vs cuFFT on one shape, same buffers, same stream, CUDA events."""
+    comps = 1 if real_in else 2
+    row = {"name": name, "shape": list(shape), "real_in": real_in}
+    try:
+        g = torch.Generator(device="cuda").manual_seed(1234)
+        x = torch.randn(tuple(shape) + (comps,), generator=g, device="cuda", dtype=torch.float32)
+        out = torch.empty(tuple(shape) + (2,), device="cuda", dtype=torch.float32)
+        plan = b200fft.plan_fft("float32", "float32", x.shape, out.shape)
+        stream = torch.cuda.current_stream().cuda_stream
+        ms = time_gpu(lambda: plan.exec(out, x, stream), warmup, steps, torch)
+        ab = algorithmic_bytes(shape, real_in)
+        row.update({"ms": ms, "gflops": flops_c2c(shape) * (0.5 if real_in else 1.0) / ms / 1e6,
+                    "gbs": ab / ms / 1e6, "hbm_frac": ab / ms / 1e6 / peak, "launches": plan.launches,
+                    "kernels": plan.describe().strip().split("\n")})
+        # parity on one batch item against numpy f64
+        ref_in = x[0].double().cpu().numpy()
+        want = np.fft.fftn(ref_in[..., 0] + (1j * ref_in[..., 1] if comps == 2 else 0))
+        got = out[0].double().cpu().numpy()
+        got = got[..., 0] + 1j * got[..., 1]
+        row["rel_l2_vs_numpy_f64"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        plan.destroy()
+        try:
+            if real_in:
+                # cuFFT R2C writes the half spectrum (cufft_benchmark.cu:34-46)
+                half = tuple(shape[:-1]) + (shape[-1] // 2 + 1, 2)
+                cout = torch.empty(half, device="cuda", dtype=torch.float32)
+            else:
+                cout = torch.empty_like(out)
+            cf = CuFFT(shape, r2c=real_in)
+            cms = time_gpu(lambda: cf.exec(x, cout, stream), warmup, steps, torch)
+            cf.destroy()
+            row.update({"cufft_ms": cms, "ours_over_cufft": ms / cms})
+            del cout
+        except Exception as e:  # cuFFT shim missing or plan failure: report, do not hide
+            row["cufft_error"] = str(e)
+        del x, out
+        torch.cuda.empty_cache()
+    except Exception as e:
+        row["error"] = "%s: %s" % (type(e).__name__, e)
+    return row
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-shapes", action="store_true", help="skip the per-shape table vs cuFFT")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import b200fft
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    peak, peak_src = measured_peak()
+    shape = PRIMARY["shape"]
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    x = torch.randn(shape + (2,), generator=g, device="cuda", dtype=torch.float32)
+    out = torch.empty_like(x)
+    plan = b200fft.plan_fft("float32", "float32", x.shape, out.shape)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        plan.exec(out, x, stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(physical_gpu_index(local)).start()
+    launches0 = b200fft.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = b200fft.launch_count() - launches0
+    clocks = sampler.stop()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if dist:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    gflops_total = world * flops_c2c(shape) / ms / 1e6
+
+    # ---- e2e: the same transform through b200fft_exec_host with pinned HOST buffers
+    h_in = torch.empty(shape + (2,), dtype=torch.float32).pin_memory()
+    h_in.copy_(x.cpu())
+    h_out = torch.empty(shape + (2,), dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    plan.exec_host(h_out.numpy(), h_in.numpy())  # warm-up (allocates the staging buffers)
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.exec_host(h_out.numpy(), h_in.numpy())
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_ok = bool(torch.allclose(h_out[:4], out[:4].cpu(), rtol=0, atol=0))
+    e2e = {"value": world * flops_c2c(shape) / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": plan.in_bytes, "d2h_bytes_per_step": plan.out_bytes,
+           "matches_device_path": e2e_ok, "api": "b200fft_exec_host (pinned host buffers, chunked 3-stream pipeline)"}
+
+    if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    ab = algorithmic_bytes(shape)
+    kernel_ms = ms / max(1, plan.launches)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(PRIMARY["name"])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": ab / plan.launches / kernel_ms / 1e6, "peak": peak, "unit": "GB/s",
+                "frac": ab / plan.launches / kernel_ms / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel": plan.describe().strip().split("\n")[0],
+                "algorithmic_bytes_per_launch": ab // plan.launches}
+
+    cpu = None
+    if not args.no_cpu:
+        import oracle
+        oracle.build()
+        cpu_ms, sample_b, threads = cpu_reference_time(shape, False, 0)
+        cpu = {"value": flops_c2c(shape) / cpu_ms / 1e6, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+               "ms_full_batch_extrapolated": cpu_ms,
+               "sample": "%d of %d transforms of length %d (oracle/ref_fft.cpp, workers=%d)" % (
+                   sample_b, shape[0], shape[1], threads)}
+
+    line = {
+        "metric": METRIC, "value": gflops_total, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": PRIMARY["name"], "per_gpu_batch": shape[0], "length": shape[1],
+                   "sharding": "batch-sharded, no collective" if world > 1 else "single GPU",
+                   "l2": "inputs+outputs %.0f MB per step > 126 MB L2 (no flush needed)" % (2 * ab / 2 / 1e6),
+                   "flop_model": "5*N*log2(N) per transform"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    del x, out, h_in, h_out
+    plan.destroy()
+    torch.cuda.empty_cache()
+
+    if not args.no_shapes and world == 1:
+        line["shapes"] = [bench_shape(n, s, r, torch, b200fft, max(5, min(args.steps, 20)), 3, peak)
+                          for n, s, r in SHAPES]
+    print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,315 @@
+// extern "C" surface of libb200fft.so (include/b200fft.h): plan construction,
+// kernel selection, execution on device or host buffers.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "plan.hpp"
+
+using namespace b200fft;
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+
+// W_N^n = exp(-/+ 2*pi*i*n/N) evaluated in double, stored in the working dtype.
+// (The reference forms theta in the working dtype, _utils.mojo:63-104; evaluating in
+// double first is strictly more accurate, and the parity tolerance covers the
+// reference's fp32-theta error, not ours.)
+int upload_twiddles(int64_t n, bool inverse, bool f64, DeviceTwiddles* out) {
+  const double sgn = inverse ? 1.0 : -1.0;
+  void* d = nullptr;
+  if (f64) {
+    std::vector<double2> h((size_t)n);
+    for (int64_t k = 0; k < n; ++k) {
+      const double th = 2.0 * M_PI * (double)k / (double)n;
+      h[(size_t)k] = make_double2(std::cos(th), sgn * std::sin(th));
+    }
+    B200_CUDA_CHECK(cudaMalloc(&d, sizeof(double2) * (size_t)n));
+    B200_CUDA_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float2> h((size_t)n);
+    for (int64_t k = 0; k < n; ++k) {
+      const double th = 2.0 * M_PI * (double)k / (double)n;
+      h[(size_t)k] = make_float2((float)std::cos(th), (float)(sgn * std::sin(th)));
+    }
+    B200_CUDA_CHECK(cudaMalloc(&d, sizeof(float2) * (size_t)n));
+    B200_CUDA_CHECK(cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice));
+  }
+  out->ptr = d;
+  out->n = n;
+  return B200FFT_OK;
+}
+
+AxisView view_of(const Problem& p, int axis) {
+  AxisView v;
+  v.n = p.axes[axis].n;
+  for (int a = 0; a < axis; ++a) v.outer_per_batch *= p.axes[a].n;
+  for (int a = axis + 1; a < p.rank; ++a) v.inner *= p.axes[a].n;
+  return v;
+}
+
+// Kernel selection. Axes run right to left like the reference (_ndim_fft_gpu.mojo:635-642);
+// the first pass reads the user's input (cast / real -> complex), the rest run in
+// place on the output. `dry` builds only the description.
+int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
+  const Problem& p = plan->prob;
+  if (p.half) return fail(B200FFT_ERR_UNSUPPORTED, "REAL_HALF is not built yet");
+  bool first = true;
+  for (int axis = p.rank - 1; axis >= 0; --axis) {
+    if (!p.axes[axis].transformed) continue;
+    const AxisView view = view_of(p, axis);
+    IoSpec src;
+    if (first) { src.dtype = p.desc.in_dtype; src.comps = p.desc.in_components; }
+    else { src.dtype = p.desc.out_dtype; src.comps = 2; }
+    if (dry) {
+      std::string radices;
+      for (uint32_t r : p.axes[axis].ordered) radices += (radices.empty() ? "" : ",") + std::to_string(r);
+      char buf[256];
+      snprintf(buf, sizeof buf, "axis %d: n=%lld inner=%lld stages=[%s]%s\n", axis, (long long)view.n,
+               (long long)view.inner, radices.c_str(), first ? " (reads input)" : " (in place)");
+      *text += buf;
+    } else {
+      std::unique_ptr<Pass> pass = make_generic_pass(*plan, axis, view, src, p.desc.inverse != 0);
+      if (!pass) return B200FFT_ERR_UNSUPPORTED;
+      pass->reads_input = first;
+      plan->passes.push_back(std::move(pass));
+    }
+    first = false;
+  }
+  return B200FFT_OK;
+}
+
+int copy_bases(const std::vector<uint32_t>& v, uint32_t* out, int cap) {
+  if (!out || (int)v.size() > cap) return -1;
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+  return (int)v.size();
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200fft_version(void) { return 100; }
+
+uint64_t b200fft_launch_count(void) { return g_launch_count.load(); }
+
+const char* b200fft_last_error(void) { return last_error().c_str(); }
+
+const char* b200fft_strerror(int status) {
+  switch (status) {
+    case B200FFT_OK: return "ok";
+    case B200FFT_ERR_INVALID_ARG: return "invalid argument";
+    case B200FFT_ERR_LAYOUT: return "layout violates the reference's layout conditions";
+    case B200FFT_ERR_BASES: return "bases do not factor the axis length";
+    case B200FFT_ERR_UNSUPPORTED: return "valid for the reference but not supported by this build";
+    case B200FFT_ERR_CUDA: return "CUDA error";
+    case B200FFT_ERR_ALLOC: return "allocation failed";
+    default: return "unknown status";
+  }
+}
+
+int b200fft_ordered_bases(uint64_t length, const uint32_t* bases, int nbases, uint32_t* out, int cap) {
+  if (!bases || nbases <= 0) return -1;
+  std::vector<uint32_t> user(bases, bases + nbases);
+  for (uint32_t b : user)
+    if (b < 2) return -1;
+  std::vector<uint32_t> o = build_ordered_bases(length, user);
+  if (!ordered_bases_valid(length, o)) return -1;
+  return copy_bases(o, out, cap);
+}
+
+int b200fft_default_bases(uint64_t length, int gpu_target, uint32_t* out, int cap) {
+  return copy_bases(estimate_best_bases(length, gpu_target != 0), out, cap);
+}
+
+int b200fft_plan_dry_run(const b200fft_desc* desc, char* buf, size_t cap) {
+  b200fft_plan tmp;
+  int rc = validate(desc, &tmp.prob);
+  if (rc != B200FFT_OK) return rc;
+  std::string text;
+  rc = build_passes(&tmp, /*dry=*/true, &text);
+  if (rc != B200FFT_OK) return rc;
+  if (buf && cap) {
+    strncpy(buf, text.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+  }
+  return B200FFT_OK;
+}
+
+int b200fft_plan_create(b200fft_plan** out, const b200fft_desc* desc) {
+  if (!out) return fail(B200FFT_ERR_INVALID_ARG, "null plan pointer");
+  *out = nullptr;
+  std::unique_ptr<b200fft_plan> plan(new b200fft_plan());
+  int rc = validate(desc, &plan->prob);
+  if (rc != B200FFT_OK) return rc;
+
+  int dev = desc->device;
+  if (dev < 0) B200_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(B200FFT_ERR_CUDA, "device %d is sm_%d%d; this library only carries sm_100a code (no fallback)", dev,
+                prop.major, prop.minor);
+  plan->device = dev;
+  plan->sm_count = prop.multiProcessorCount;
+  DeviceGuard guard(dev);
+
+  const bool f64 = desc->out_dtype == B200FFT_F64;
+  plan->tw.resize(plan->prob.rank);
+  for (int a = 0; a < plan->prob.rank; ++a) {
+    if (!plan->prob.axes[a].transformed) continue;
+    rc = upload_twiddles(plan->prob.axes[a].n, desc->inverse != 0, f64, &plan->tw[a]);
+    if (rc != B200FFT_OK) { b200fft_plan_destroy(plan.release()); return rc; }
+  }
+  rc = build_passes(plan.get(), /*dry=*/false, nullptr);
+  if (rc != B200FFT_OK) { b200fft_plan_destroy(plan.release()); return rc; }
+  *out = plan.release();
+  return B200FFT_OK;
+}
+
+int b200fft_plan_destroy(b200fft_plan* plan) {
+  if (!plan) return B200FFT_OK;
+  DeviceGuard guard(plan->device);
+  for (auto& t : plan->tw)
+    if (t.ptr) cudaFree(t.ptr);
+  for (void* p : plan->owned_device)
+    if (p) cudaFree(p);
+  if (plan->workspace) cudaFree(plan->workspace);
+  for (int i = 0; i < 2; ++i) {
+    if (plan->h_dev_in[i]) cudaFree(plan->h_dev_in[i]);
+    if (plan->h_dev_out[i]) cudaFree(plan->h_dev_out[i]);
+  }
+  for (int i = 0; i < 3; ++i)
+    if (plan->hs[i]) cudaStreamDestroy(plan->hs[i]);
+  for (auto& e : plan->h_ev)
+    if (e) cudaEventDestroy(e);
+  delete plan;
+  return B200FFT_OK;
+}
+
+static int run_passes(b200fft_plan* plan, void* d_out, const void* d_in, int64_t nbatch, cudaStream_t st) {
+  const Problem& p = plan->prob;
+  const size_t in_stride = (size_t)p.in_scalars_per_batch * p.in_elem;
+  const size_t out_stride = (size_t)p.out_scalars_per_batch * p.out_elem;
+  const int64_t chunk = plan->chunk_batches > 0 ? plan->chunk_batches : nbatch;
+  for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
+    const int64_t nb = std::min<int64_t>(chunk, nbatch - b0);
+    char* out_b = (char*)d_out + (size_t)b0 * out_stride;
+    const char* in_b = (const char*)d_in + (size_t)b0 * in_stride;
+    for (auto& pass : plan->passes) {
+      int rc = pass->launch(pass->reads_input ? (const void*)in_b : (const void*)out_b, out_b, nb, st);
+      if (rc != B200FFT_OK) return rc;
+    }
+  }
+  return B200FFT_OK;
+}
+
+int b200fft_exec(b200fft_plan* plan, void* d_out, const void* d_in, void* cu_stream) {
+  if (!plan || !d_out || !d_in) return fail(B200FFT_ERR_INVALID_ARG, "null plan or buffer");
+  DeviceGuard guard(plan->device);
+  return run_passes(plan, d_out, d_in, plan->prob.batch, (cudaStream_t)cu_stream);
+}
+
+int b200fft_exec_scatter(b200fft_plan*, void* const*, int, int, const void*, void*) {
+  return fail(B200FFT_ERR_UNSUPPORTED, "exec_scatter is not built yet");
+}
+
+// Host-buffer execution: the batch is cut into chunks that flow through
+// H2D (stream 0) -> kernels (stream 1) -> D2H (stream 2) with two device buffers
+// per direction, so PCIe transfers in both directions overlap the kernels.
+int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in) {
+  if (!plan || !h_out || !h_in) return fail(B200FFT_ERR_INVALID_ARG, "null plan or buffer");
+  DeviceGuard guard(plan->device);
+  const Problem& p = plan->prob;
+  const size_t in_stride = (size_t)p.in_scalars_per_batch * p.in_elem;
+  const size_t out_stride = (size_t)p.out_scalars_per_batch * p.out_elem;
+  if (!plan->host_ready) {
+    // ~8 chunks, at least 1 batch item each, at most 256 MiB of output per chunk
+    int64_t chunk = std::max<int64_t>(1, (p.batch + 7) / 8);
+    const size_t cap = (size_t)256 << 20;
+    while (chunk > 1 && (size_t)chunk * std::max(in_stride, out_stride) > cap) chunk = (chunk + 1) / 2;
+    if (plan->chunk_batches > 0) chunk = ((chunk + plan->chunk_batches - 1) / plan->chunk_batches) * plan->chunk_batches;
+    plan->host_chunk = chunk;
+    for (int i = 0; i < 3; ++i) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->hs[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      B200_CUDA_CHECK(cudaMalloc(&plan->h_dev_in[i], (size_t)chunk * in_stride));
+      B200_CUDA_CHECK(cudaMalloc(&plan->h_dev_out[i], (size_t)chunk * out_stride));
+    }
+    for (auto& e : plan->h_ev) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    plan->host_ready = true;
+  }
+  cudaEvent_t* ev_in = &plan->h_ev[0];    // [2] H2D done
+  cudaEvent_t* ev_k = &plan->h_ev[2];     // [2] kernels done
+  cudaEvent_t* ev_out = &plan->h_ev[4];   // [2] D2H done
+  const int64_t chunk = plan->host_chunk;
+  int64_t k = 0;
+  for (int64_t b0 = 0; b0 < p.batch; b0 += chunk, ++k) {
+    const int slot = (int)(k & 1);
+    const int64_t nb = std::min<int64_t>(chunk, p.batch - b0);
+    if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[0], ev_k[slot], 0));  // input slot consumed
+    B200_CUDA_CHECK(cudaMemcpyAsync(plan->h_dev_in[slot], (const char*)h_in + (size_t)b0 * in_stride,
+                                    (size_t)nb * in_stride, cudaMemcpyHostToDevice, plan->hs[0]));
+    B200_CUDA_CHECK(cudaEventRecord(ev_in[slot], plan->hs[0]));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[1], ev_in[slot], 0));
+    if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[1], ev_out[slot], 0));  // output slot drained
+    int rc = run_passes(plan, plan->h_dev_out[slot], plan->h_dev_in[slot], nb, plan->hs[1]);
+    if (rc != B200FFT_OK) return rc;
+    B200_CUDA_CHECK(cudaEventRecord(ev_k[slot], plan->hs[1]));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[2], ev_k[slot], 0));
+    B200_CUDA_CHECK(cudaMemcpyAsync((char*)h_out + (size_t)b0 * out_stride, plan->h_dev_out[slot],
+                                    (size_t)nb * out_stride, cudaMemcpyDeviceToHost, plan->hs[2]));
+    B200_CUDA_CHECK(cudaEventRecord(ev_out[slot], plan->hs[2]));
+  }
+  B200_CUDA_CHECK(cudaStreamSynchronize(plan->hs[2]));
+  return B200FFT_OK;
+}
+
+size_t b200fft_plan_workspace_bytes(const b200fft_plan* plan) { return plan ? plan->workspace_bytes : 0; }
+
+int b200fft_plan_get_bases(const b200fft_plan* plan, int axis, uint32_t* out, int cap) {
+  if (!plan || axis < 0 || axis >= plan->prob.rank) return -1;
+  return copy_bases(plan->prob.axes[axis].ordered, out, cap);
+}
+
+size_t b200fft_plan_describe(const b200fft_plan* plan, char* buf, size_t cap) {
+  if (!plan) return 0;
+  std::string text;
+  for (auto& pass : plan->passes) text += pass->describe() + "\n";
+  if (plan->chunk_batches > 0) text += "chunk_batches=" + std::to_string(plan->chunk_batches) + "\n";
+  if (buf && cap) {
+    strncpy(buf, text.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+  }
+  return text.size() + 1;
+}
+
+int b200fft_plan_launches(const b200fft_plan* plan) {
+  if (!plan) return 0;
+  int per_chunk = 0;
+  for (auto& pass : plan->passes) per_chunk += pass->launches();
+  const int64_t chunk = plan->chunk_batches > 0 ? plan->chunk_batches : plan->prob.batch;
+  return per_chunk * (int)((plan->prob.batch + chunk - 1) / chunk);
+}
+
+size_t b200fft_plan_in_bytes(const b200fft_plan* plan) {
+  return plan ? (size_t)plan->prob.batch * plan->prob.in_scalars_per_batch * plan->prob.in_elem : 0;
+}
+size_t b200fft_plan_out_bytes(const b200fft_plan* plan) {
+  return plan ? (size_t)plan->prob.batch * plan->prob.out_scalars_per_batch * plan->prob.out_elem : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// Plan = validated problem + device twiddle tables + an ordered list of kernel passes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "planner.hpp"
+
+namespace b200fft {
+
+// The 1-D sub-transforms of one axis inside a dense row-major (batch, dims...) array:
+// element (o, n, i) lives at (o*N + n)*inner + i, with outer = batch * prod(dims before
+// the axis) and inner = prod(dims after it). inner == 1 is the contiguous-row case.
+struct AxisView {
+  int64_t outer_per_batch = 1;  // prod(dims before axis)
+  int64_t n = 0;                // axis length
+  int64_t inner = 1;            // prod(dims after axis) = element stride along the axis
+};
+
+// Where a pass reads from: the user's input (any dtype, real or complex) or the
+// working complex buffer (out dtype).
+struct IoSpec {
+  int dtype = B200FFT_F32;  // scalar type
+  int comps = 2;            // 1 real, 2 interleaved complex
+};
+
+// Peer scatter for the slab exchange fused into the last pass's store.
+struct Scatter {
+  void* const* peer_out = nullptr;  // device-visible array of npeers base pointers (device memory)
+  int npeers = 0;
+  int my_rank = 0;
+};
+
+struct Pass {
+  virtual ~Pass() {}
+  // Run this pass for `nbatch` batch items. src/dst already point at the first item.
+  virtual int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) = 0;
+  virtual std::string describe() const = 0;
+  virtual int launches() const { return 1; }
+  bool reads_input = false;  // src is the user's input buffer (else: dst, in place)
+};
+
+struct DeviceTwiddles {
+  void* ptr = nullptr;  // out-dtype complex W_N^n, n in [0, N)
+  int64_t n = 0;
+};
+
+}  // namespace b200fft
+
+struct b200fft_plan {
+  b200fft::Problem prob;
+  int device = 0;
+  int sm_count = 148;
+  std::vector<b200fft::DeviceTwiddles> tw;  // one per axis (null for skipped axes)
+  std::vector<std::unique_ptr<b200fft::Pass>> passes;
+  std::vector<void*> owned_device;          // misc device allocations freed at destroy
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  int64_t chunk_batches = 0;  // >0: run all passes per chunk of this many batch items (L2 residency)
+  // exec_host resources (lazily created)
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  void* h_dev_in[2] = {nullptr, nullptr};
+  void* h_dev_out[2] = {nullptr, nullptr};
+  cudaEvent_t h_ev[8] = {};
+  int64_t host_chunk = 0;
+  bool host_ready = false;
+};
+
+namespace b200fft {
+
+// kernel families (each returns nullptr when it does not cover the request)
+std::unique_ptr<Pass> make_generic_pass(const b200fft_plan& plan, int axis, const AxisView& view,
+                                        const IoSpec& src, bool scale_inverse);
+
+}  // namespace b200fft

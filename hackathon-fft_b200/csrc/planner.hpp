@@ -1,0 +1,44 @@
+// Host planner: the reference's compile-time plan rules restated as runtime code.
+//   base ordering / validity   fft/fft/_utils.mojo:125-221
+//   default bases              fft/fft/fft.mojo:49-104
+//   layout conditions          fft/fft/fft.mojo:20-46
+// Pure C++ (no CUDA) so it is testable without a GPU.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+
+namespace b200fft {
+
+uint64_t times_divisible(uint64_t length, uint64_t base);
+std::vector<uint32_t> build_ordered_bases(uint64_t length, std::vector<uint32_t> bases);
+bool ordered_bases_valid(uint64_t length, const std::vector<uint32_t>& ordered);
+std::vector<uint32_t> estimate_best_bases(uint64_t length, bool gpu_target);
+
+// One transformed (or skipped) axis of a validated descriptor.
+struct AxisSpec {
+  int64_t n = 0;                  // logical transform length
+  bool transformed = true;        // axis_mask bit
+  std::vector<uint32_t> user;     // user bases (after defaults)
+  std::vector<uint32_t> ordered;  // canonical descending stage list
+};
+
+// A validated descriptor: everything the kernel chooser needs.
+struct Problem {
+  b200fft_desc desc;            // copy (bases pointers cleared)
+  int rank = 0;
+  int64_t batch = 0;
+  std::vector<AxisSpec> axes;   // size rank
+  bool half = false;            // B200FFT_REAL_HALF
+  // element counts per batch item (scalars of in/out dtype)
+  int64_t in_scalars_per_batch = 0, out_scalars_per_batch = 0;
+  size_t in_elem = 0, out_elem = 0;  // bytes per scalar
+};
+
+// Mirrors _check_layout_conditions_nd + the bases asserts. Returns a status code
+// and leaves the detail in last_error().
+int validate(const b200fft_desc* d, Problem* out);
+
+}  // namespace b200fft

@@ -1,0 +1,156 @@
+/*
+ * b200fft — C ABI of the B200-native batched N-d radix-n FFT.
+ *
+ * This is the drop-in boundary for martinvuyk/hackathon-fft's `fft` package. The
+ * reference has no FFI of its own: its public surface is four Mojo generics in
+ * fft/fft/fft.mojo (plan_fft x2, fft x2) whose GPU overloads end in
+ * `_run_gpu_nd_fft` (fft/fft/_ndim_fft_gpu.mojo:462-642). Everything those
+ * overloads take as compile-time parameters (dtypes, layouts incl. batch,
+ * inverse, bases) becomes a runtime descriptor here; the Mojo wrappers in
+ * hackathon-fft_b200/mojo/fft/ read the parameters off and call these entry
+ * points with `external_call`.
+ *
+ * All functions are `extern "C"`, take plain pointers and sizes, never throw or
+ * abort across the ABI, and return an int status (0 = B200FFT_OK). Distinct
+ * plans may be used from distinct threads; one plan must not be executed
+ * concurrently with itself (same rule as the reference, whose plan owns mutable
+ * scratch: fft/fft/_ndim_fft_cpu.mojo:39-45, _ndim_fft_gpu.mojo:176-185).
+ *
+ * There is no CPU fallback: every entry point that computes fails with
+ * B200FFT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef B200FFT_H
+#define B200FFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200FFT_API __attribute__((visibility("default")))
+#else
+#define B200FFT_API
+#endif
+
+#define B200FFT_MAX_RANK 8
+
+/* status codes */
+enum {
+  B200FFT_OK = 0,
+  B200FFT_ERR_INVALID_ARG = 1, /* NULL pointer, rank/batch out of range                      */
+  B200FFT_ERR_LAYOUT = 2,      /* violates _check_layout_conditions_nd (fft.mojo:20-46)      */
+  B200FFT_ERR_BASES = 3,       /* bases do not multiply to the axis length / contain 1
+                                  (_utils.mojo:205-220 compile-time asserts)                 */
+  B200FFT_ERR_UNSUPPORTED = 4, /* valid for the reference, not built yet here (see message)  */
+  B200FFT_ERR_CUDA = 5,        /* CUDA runtime / driver error, or no sm_100 device           */
+  B200FFT_ERR_ALLOC = 6
+};
+
+/* scalar types of the interleaved buffers (the reference's in_dtype / out_dtype parameters) */
+enum { B200FFT_U8 = 0, B200FFT_F32 = 1, B200FFT_F64 = 2 };
+
+/* real-input / real-output packing */
+enum {
+  /* Reference semantics (_fft.mojo:254-255): in_components == 1 feeds reals into
+     stage 0 of the last axis and the output is the FULL N-bin complex spectrum. */
+  B200FFT_REAL_FULL = 0,
+  /* cuFFT-style half spectrum (new functionality, north-star piece 3):
+     forward: real (.., n_last) -> complex (.., n_last/2+1);
+     inverse: complex (.., n_last/2+1) -> real (.., n_last), scaled 1/prod(dims). */
+  B200FFT_REAL_HALF = 1
+};
+
+/* plan flags */
+enum {
+  /* Force the generic runtime-radix kernel for every axis (debug knob; plays the
+     role of the reference's `_test: _GPUTest` path forcer, _ndim_fft_gpu.mojo:453-459). */
+  B200FFT_FLAG_FORCE_GENERIC = 1u << 0,
+  /* Disable L2-resident chunking of multi-pass N-d transforms. */
+  B200FFT_FLAG_NO_CHUNKING = 1u << 1
+};
+
+/*
+ * Runtime form of plan_fft's compile-time parameters (fft.mojo:122-132,160-176).
+ * Buffers are dense row-major `(batch, dims[0..rank-1], components)`, interleaved
+ * re/im, exactly the LayoutTensor layouts the reference requires.
+ */
+typedef struct b200fft_desc {
+  int32_t rank;                   /* number of non-batch axes, 1..B200FFT_MAX_RANK             */
+  int64_t dims[B200FFT_MAX_RANK]; /* out_layout.shape[1:rank+1]; each >= 2                     */
+  int64_t batch;                  /* out_layout.shape[0] >= 1                                  */
+  int32_t in_components;          /* in_layout last dim: 1 (real) or 2 (complex)               */
+  int32_t in_dtype;               /* B200FFT_U8 | F32 | F64 (cast on load, _fft.mojo:257)      */
+  int32_t out_dtype;              /* B200FFT_F32 | F64                                         */
+  int32_t inverse;                /* 0 forward (unnormalised), 1 inverse (x 1/prod(dims))      */
+  int32_t real_mode;              /* B200FFT_REAL_FULL | B200FFT_REAL_HALF                     */
+  uint32_t axis_mask;             /* bit a set = transform axis a; 0 = all axes (reference).
+                                     Used by the slab decomposition (local 2-D, then z pass).  */
+  const uint32_t* bases;          /* user radix bases of all axes, concatenated; NULL = the
+                                     reference's GPU default rule (fft.mojo:49-104)            */
+  const int32_t* bases_count;     /* [rank] number of bases per axis (0 = default for that axis) */
+  int32_t device;                 /* CUDA ordinal, or -1 for the current device                */
+  uint32_t flags;                 /* B200FFT_FLAG_*                                            */
+} b200fft_desc;
+
+typedef struct b200fft_plan b200fft_plan;
+
+/* ---- plan_fft[...](ctx=ctx)  (fft.mojo:160-210 -> _GPUPlan.__init__, _ndim_fft_gpu.mojo:179-207)
+ * Validates the layout and bases, chooses kernels, uploads the twiddle tables. */
+B200FFT_API int b200fft_plan_create(b200fft_plan** plan, const b200fft_desc* desc);
+
+/* ---- fft(output, x, ctx, plan=plan)  (fft.mojo:262-323 -> _run_gpu_nd_fft, _ndim_fft_gpu.mojo:462-642)
+ * Asynchronous on `cu_stream` (a CUstream / cudaStream_t; NULL = default stream);
+ * the caller synchronises, as bench.mojo:51-52 does. `d_out` and `d_in` are device
+ * pointers; out-of-place, or in-place (d_out == d_in) when input and output have the
+ * same element type and component count. */
+B200FFT_API int b200fft_exec(b200fft_plan* plan, void* d_out, const void* d_in, void* cu_stream);
+
+/* Same transform with HOST buffers: pinned staging, chunked H2D -> kernels -> D2H
+ * overlapped on internal streams; returns after the result is in h_out. This is the
+ * end-to-end call bench.py times as `e2e`. */
+B200FFT_API int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in);
+
+/* Slab-decomposition helper (multi-GPU, one process per GPU): run the plan but store
+ * the result of the LAST pass directly into peer-mapped buffers. Output element with
+ * index y along axis `split_axis` goes to peer_out[y / (dims[split_axis]/npeers)], at the
+ * position it has in that peer's [.., y_local, ..] slab (slab exchange). */
+B200FFT_API int b200fft_exec_scatter(b200fft_plan* plan, void* const* peer_out, int npeers, int my_rank,
+                         const void* d_in, void* cu_stream);
+
+B200FFT_API int b200fft_plan_destroy(b200fft_plan* plan);
+
+/* ---- introspection (tests, harness) */
+B200FFT_API size_t b200fft_plan_workspace_bytes(const b200fft_plan* plan);
+/* ordered stage list of an axis, the reference's `_get_ordered_bases_processed_list`
+ * (_utils.mojo:186-221); returns the count or -1 */
+B200FFT_API int b200fft_plan_get_bases(const b200fft_plan* plan, int axis, uint32_t* out, int cap);
+/* human-readable list of the kernel passes the plan launches; returns bytes needed */
+B200FFT_API size_t b200fft_plan_describe(const b200fft_plan* plan, char* buf, size_t cap);
+/* number of kernel launches one b200fft_exec performs */
+B200FFT_API int b200fft_plan_launches(const b200fft_plan* plan);
+/* in/out buffer sizes in bytes for one exec */
+B200FFT_API size_t b200fft_plan_in_bytes(const b200fft_plan* plan);
+B200FFT_API size_t b200fft_plan_out_bytes(const b200fft_plan* plan);
+
+/* ---- host-side planner rules, usable without a GPU */
+/* `_build_ordered_bases` + validity asserts (_utils.mojo:163-221); count or -1 if rejected */
+B200FFT_API int b200fft_ordered_bases(uint64_t length, const uint32_t* bases, int nbases, uint32_t* out, int cap);
+/* `_estimate_best_bases` (fft.mojo:49-104); gpu_target != 0 selects the GPU rule */
+B200FFT_API int b200fft_default_bases(uint64_t length, int gpu_target, uint32_t* out, int cap);
+/* validate a descriptor and write the pass list it would produce, without touching CUDA */
+B200FFT_API int b200fft_plan_dry_run(const b200fft_desc* desc, char* buf, size_t cap);
+
+/* ---- errors / bookkeeping */
+B200FFT_API const char* b200fft_strerror(int status);
+B200FFT_API const char* b200fft_last_error(void); /* thread-local detail of the last failure */
+B200FFT_API int b200fft_version(void);
+/* total kernels launched by this library in this process (bench.py's gpu_launches) */
+B200FFT_API uint64_t b200fft_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FFT_H */

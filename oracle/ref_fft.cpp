@@ -233,27 +233,80 @@ struct Src {
 // One Stockham stage over a whole row (_fft.mojo:228-296 / :331-391):
 //   u = i mod Q, n = (i div Q)*P + (u mod P)
 //   acc = X[n]; for j in 1..r-1: acc = fma(W[((j*u) mod Q)*rho], X[n + j*N/r], acc)
-template <class T>
-void run_stage(const AxisPlan<T>& ax, size_t s, bool inverse, const Src<T>& x, Cx<T>* out) {
-  const u64 N = ax.N, r = ax.radix[s], P = ax.processed[s], Q = P * r, rho = N / Q, step = N / r;
-  const bool real_in = (x.c == nullptr && x.comps == 1);
-  const bool last = (Q == N);
+// The output index is walked as i = q*Q + k*P + p (q < N/Q, k < r, p < P), which gives
+// u = k*P + p and n = q*P + p without a division per point; the arithmetic per output
+// point (operands, order of the FMAs) is exactly the reference's. R > 0 fixes the radix
+// at compile time so the j loop unrolls like the reference's `comptime for`.
+template <class T, int R, bool UNROLLED, bool REAL_IN, class Getter>
+void run_stage_impl(const AxisPlan<T>& ax, size_t s, bool inverse, Getter get, Cx<T>* out) {
+  const u64 N = ax.N, r = R > 0 ? (u64)R : ax.radix[s], P = ax.processed[s], Q = P * r, rho = N / Q,
+            step = N / r;
+  const bool scale = inverse && (Q == N);
   const T inv_n = (T)(1.0 / (double)N);
-  for (u64 i = 0; i < N; ++i) {
-    const u64 u = i % Q;
-    const u64 n = (i / Q) * P + (u % P);
-    Cx<T> acc = x.get(n);
-    for (u64 j = 1; j < r; ++j) {
-      const Cx<T> w = ax.tw[((j * u) % Q) * rho];
-      if (ax.unrolled) {
-        if (real_in) acc = unit_phasor_fma_real(w, x.get(n + j * step).re, acc, j == 1);
-        else acc = unit_phasor_fma(w, x.get(n + j * step), acc);
-      } else {
-        acc = cfma(w, x.get(n + j * step), acc);
+  const Cx<T>* tw = ax.tw.data();
+  for (u64 q = 0; q < N / Q; ++q) {
+    for (u64 k = 0; k < r; ++k) {
+      const u64 i0 = q * Q + k * P, n0 = q * P;
+      for (u64 p = 0; p < P; ++p) {
+        const u64 u = k * P + p, n = n0 + p;
+        Cx<T> acc = get(n);
+        u64 ju = 0;
+        for (u64 j = 1; j < r; ++j) {
+          ju += u;
+          if (ju >= Q) ju -= Q;  // (j*u) mod Q, since u < Q
+          const Cx<T> w = tw[ju * rho];
+          if (UNROLLED) {
+            if (REAL_IN) acc = unit_phasor_fma_real(w, get(n + j * step).re, acc, j == 1);
+            else acc = unit_phasor_fma(w, get(n + j * step), acc);
+          } else {
+            acc = cfma(w, get(n + j * step), acc);
+          }
+        }
+        if (scale) { acc.re *= inv_n; acc.im *= inv_n; }
+        out[i0 + p] = acc;
       }
     }
-    if (inverse && last) { acc.re *= inv_n; acc.im *= inv_n; }
-    out[i] = acc;
+  }
+}
+
+template <class T, bool UNROLLED, bool REAL_IN, class Getter>
+void run_stage_radix(const AxisPlan<T>& ax, size_t s, bool inverse, Getter get, Cx<T>* out) {
+  switch (ax.radix[s]) {
+    case 2: return run_stage_impl<T, 2, UNROLLED, REAL_IN>(ax, s, inverse, get, out);
+    case 3: return run_stage_impl<T, 3, UNROLLED, REAL_IN>(ax, s, inverse, get, out);
+    case 4: return run_stage_impl<T, 4, UNROLLED, REAL_IN>(ax, s, inverse, get, out);
+    case 5: return run_stage_impl<T, 5, UNROLLED, REAL_IN>(ax, s, inverse, get, out);
+    case 7: return run_stage_impl<T, 7, UNROLLED, REAL_IN>(ax, s, inverse, get, out);
+    case 8: return run_stage_impl<T, 8, UNROLLED, REAL_IN>(ax, s, inverse, get, out);
+    default: return run_stage_impl<T, 0, UNROLLED, REAL_IN>(ax, s, inverse, get, out);
+  }
+}
+
+template <class T>
+void run_stage(const AxisPlan<T>& ax, size_t s, bool inverse, const Src<T>& x, Cx<T>* out) {
+  if (x.c) {  // working-dtype complex buffer: the common case
+    const Cx<T>* c = x.c;
+    auto get = [c](u64 i) { return c[i]; };
+    if (ax.unrolled) run_stage_radix<T, true, false>(ax, s, inverse, get, out);
+    else run_stage_radix<T, false, false>(ax, s, inverse, get, out);
+    return;
+  }
+  if (x.comps == 2 && x.dt == (sizeof(T) == 4 ? IN_F32 : IN_F64)) {  // complex input already in T
+    const Cx<T>* c = reinterpret_cast<const Cx<T>*>(x.raw);
+    auto get = [c](u64 i) { return c[i]; };
+    if (ax.unrolled) run_stage_radix<T, true, false>(ax, s, inverse, get, out);
+    else run_stage_radix<T, false, false>(ax, s, inverse, get, out);
+    return;
+  }
+  auto get = [x](u64 i) { return x.get(i); };
+  if (x.comps == 1) {
+    // real input: the unrolled path uses the real-operand FMA forms (_utils.mojo:349-372);
+    // the runtime path widens to (x, 0) and uses the complex FMA (_fft.mojo:254-255)
+    if (ax.unrolled) run_stage_radix<T, true, true>(ax, s, inverse, get, out);
+    else run_stage_radix<T, false, false>(ax, s, inverse, get, out);
+  } else {
+    if (ax.unrolled) run_stage_radix<T, true, false>(ax, s, inverse, get, out);
+    else run_stage_radix<T, false, false>(ax, s, inverse, get, out);
   }
 }
 

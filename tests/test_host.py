@@ -1,0 +1,116 @@
+"""CPU-only checks of the boundary: the C-ABI library loads, exports every symbol
+include/b200fft.h declares, and its host planner reproduces the reference's
+compile-time plan rules (compared with the oracle's independent restatement)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import b200fft
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200fft.h")).read()
+    return sorted(set(re.findall(r"B200FFT_API[^;]*?\b(b200fft_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    L = ctypes.CDLL(b200fft.lib_path())
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(s[0] for s in b200fft.SYMBOLS) == declared  # the shim binds exactly the header
+    assert b200fft.lib().b200fft_version() >= 100
+
+
+def test_strerror():
+    assert b200fft.lib().b200fft_strerror(0) == b"ok"
+    assert b"bases" in b200fft.lib().b200fft_strerror(3)
+
+
+LENGTHS = [2, 3, 4, 5, 6, 7, 8, 10, 16, 20, 21, 30, 32, 35, 48, 60, 64, 93, 100, 128, 194, 480, 512, 640, 1024, 4096]
+
+
+@pytest.mark.parametrize("n", LENGTHS)
+def test_default_bases_match_oracle(oracle, n):
+    for target in ("cpu", "gpu"):
+        assert b200fft.default_bases(n, target) == oracle.default_bases(n, target)
+
+
+def test_ordered_bases_golden_cases(oracle, golden):
+    for case in golden["cases_1d"]:
+        got = b200fft.ordered_bases(case["length"], case["bases"])
+        assert got == oracle.ordered_bases(case["length"], case["bases"])
+        assert int(np.prod(got)) == case["length"]
+        assert got == sorted(got, reverse=True)
+
+
+def test_ordered_bases_random_match_oracle(oracle):
+    rng = np.random.default_rng(0)
+    pool = [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 16, 20, 31, 32, 97]
+    for _ in range(400):
+        k = int(rng.integers(1, 4))
+        bases = [int(b) for b in rng.choice(pool, size=k, replace=False)]
+        n = 1
+        for b in bases:
+            n *= b ** int(rng.integers(0, 3))
+        n = max(n, 2)
+        assert b200fft.ordered_bases(n, bases) == oracle.ordered_bases(n, bases), (n, bases)
+
+
+def test_rejected_bases():
+    assert b200fft.ordered_bases(60, [7, 2]) is None
+    assert b200fft.ordered_bases(8, [1, 2]) is None
+    assert b200fft.ordered_bases(93, [3]) is None
+
+
+def test_dry_run_layout_conditions():
+    """_check_layout_conditions_nd (fft.mojo:20-46) as runtime errors."""
+    ok = b200fft.dry_run("float32", "float32", (4, 128, 2), (4, 128, 2))
+    assert "stages=[2,2,2,2,2,2,2]" in ok
+    txt = b200fft.dry_run("uint8", "float64", (1, 6, 4, 8, 1), (1, 6, 4, 8, 2))
+    assert txt.splitlines()[0].startswith("axis 2") and "reads input" in txt.splitlines()[0]
+    assert txt.splitlines()[-1].startswith("axis 0")
+    with pytest.raises(b200fft.B200FFTError) as e:
+        b200fft.dry_run("float32", "float32", (4, 2), (4, 2))
+    assert e.value.status == 2
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.dry_run("float32", "float32", (4, 8, 3), (4, 8, 2))       # in last dim must be 1|2
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.dry_run("float32", "float32", (4, 8, 2), (4, 8, 1))       # out last dim must be 2
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.dry_run("float32", "float32", (4, 8, 2), (4, 9, 2))       # equal leading shape
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.dry_run("float32", "float32", (4, 1, 8, 2), (4, 1, 8, 2))  # no inner dim of size 1
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.dry_run("float32", "uint8", (4, 8, 2), (4, 8, 2))         # out dtype must be float
+    with pytest.raises(b200fft.B200FFTError) as e:
+        b200fft.dry_run("float32", "float32", (4, 60, 2), (4, 60, 2), bases=[[7, 2]])
+    assert e.value.status == 3 and "only able to produce" in str(e.value)
+    with pytest.raises(b200fft.B200FFTError) as e:
+        b200fft.dry_run("float32", "float32", (4, 8, 8, 2), (4, 8, 8, 2), bases=[[2]])
+    assert e.value.status == 3                                            # one bases list per axis
+
+
+def test_user_bases_reach_the_plan():
+    txt = b200fft.dry_run("float32", "float32", (2, 93, 2), (2, 93, 2), bases=[[3, 31]])
+    assert "stages=[31,3]" in txt
+    txt = b200fft.dry_run("float32", "float32", (2, 128, 2), (2, 128, 2), bases=[[16, 8]])
+    assert "stages=[16,8]" in txt
+    txt = b200fft.dry_run("float32", "float32", (2, 60, 48, 2), (2, 60, 48, 2), bases=[[6, 5, 2], [3, 2]])
+    assert "stages=[6,5,2]" in txt and "stages=[3,2,2,2,2]" in txt
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(b200fft.B200FFTError) as e:
+        b200fft.plan_fft("float32", "float32", (2, 8, 2), (2, 8, 2))
+    assert e.value.status == 5
