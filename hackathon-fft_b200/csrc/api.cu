@@ -83,7 +83,9 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
                (long long)view.inner, radices.c_str(), first ? " (reads input)" : " (in place)");
       *text += buf;
     } else {
-      std::unique_ptr<Pass> pass = make_generic_pass(*plan, axis, view, src, p.desc.inverse != 0);
+      std::unique_ptr<Pass> pass;
+      if (!(p.desc.flags & B200FFT_FLAG_FORCE_GENERIC)) pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0);
+      if (!pass) pass = make_generic_pass(*plan, axis, view, src, p.desc.inverse != 0);
       if (!pass) return B200FFT_ERR_UNSUPPORTED;
       pass->reads_input = first;
       plan->passes.push_back(std::move(pass));

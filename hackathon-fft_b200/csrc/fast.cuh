@@ -1,0 +1,261 @@
+// Compile-time Stockham kernels: every radix, stride and index is a template constant.
+//
+// A transform of length N is a fixed list of super-stages R_0..R_{S-1} (prod = N). Stage s
+// has P_s = prod_{t<s} R_t, Q_s = P_s*R_s and N/R_s butterflies; butterfly n reads
+//     x_j = X[n + j*N/R_s] * W_{Q_s}^{j*(n mod P_s)}          (reference: _fft.mojo:233-267)
+// runs the register codelet Dft<R_s> (dft.cuh) and writes Y[(n div P_s)*Q_s + (n mod P_s) + k*P_s].
+// Stage 0 reads global memory directly, the last stage writes global memory directly, and
+// the S-1 exchanges in between go through shared memory (ping-pong buffers, padded so the
+// scatter writes of small-P stages do not bank-conflict). Global memory is touched exactly
+// once per element per pass.
+//
+// One stage template serves three tile shapes through an (outer o, axis index i, inner c)
+// index space, c fastest in the butterfly enumeration so a warp's accesses are contiguous:
+//   rows   : O = rows per tile, CN = 1     (contiguous 1-D transforms)
+//   cols   : O = 1, CN = columns per tile  (strided axis; no transpose kernel)
+//   planes : both, back to back, for 2-D tiles that fit shared memory
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dft.cuh"
+
+namespace b200fft {
+
+template <int... Rs>
+struct Radices {
+  static constexpr int count = sizeof...(Rs);
+  static constexpr int r[sizeof...(Rs)] = {Rs...};
+  static constexpr int product() {
+    int p = 1;
+    for (int i = 0; i < count; ++i) p *= r[i];
+    return p;
+  }
+  static constexpr int processed(int s) {  // P_s
+    int p = 1;
+    for (int i = 0; i < s; ++i) p *= r[i];
+    return p;
+  }
+  // offset of stage s in the per-plan twiddle table: stages >= 1 store (R_s - 1) * P_s entries
+  static constexpr int tw_offset(int s) {
+    int off = 0;
+    for (int i = 1; i < s; ++i) off += (r[i] - 1) * processed(i);
+    return off;
+  }
+  static constexpr int tw_total() { return tw_offset(count); }
+  static constexpr int max_radix() {
+    int m = 0;
+    for (int i = 0; i < count; ++i) m = r[i] > m ? r[i] : m;
+    return m;
+  }
+};
+
+// ---- shared-memory exchange layouts --------------------------------------------------------
+// rows: element i of row o. After a stage with P < 16 the scatter stride between consecutive
+// butterflies is Q (a power of two for the hot sizes): one pad of P elements per Q-block makes
+// it odd in units of P, which removes the bank conflicts (exchange padding).
+template <int N, int Q, int P>
+struct RowLayout {
+  static constexpr bool padded = (P < 16) && (Q % 2 == 0) && (Q < N);
+  static constexpr int stride = padded ? N + (N / Q) * P : N;
+  static constexpr int size(int rows) { return rows * stride; }
+  static __device__ __forceinline__ int off(int o, int i, int) {
+    if constexpr (padded) return o * stride + i + (i / Q) * P;
+    else return o * stride + i;
+  }
+};
+// cols / planes: dense [i][c], c contiguous: conflict-free without padding when CN >= 16
+template <int N, int CN>
+struct DenseLayout {
+  static constexpr int size(int) { return N * CN; }
+  static __device__ __forceinline__ int off(int, int i, int c) { return i * CN + c; }
+};
+
+// ---- global accessors ------------------------------------------------------------------------
+// element (o, i, c) of the tile lives at base[o*so + i*si + c]; rows/columns beyond the valid
+// extent (ragged last tile) read as zero and are not written.
+template <bool REAL>
+struct GlobalSrc {
+  const void* __restrict__ base;
+  long long so, si;
+  int valid_o, valid_c;
+  __device__ __forceinline__ float2 load(int o, int i, int c) const {
+    if (o >= valid_o || c >= valid_c) return make_float2(0.f, 0.f);
+    const long long idx = o * so + i * si + c;
+    if constexpr (REAL) return make_float2(__ldg(reinterpret_cast<const float*>(base) + idx), 0.f);
+    else return __ldg(reinterpret_cast<const float2*>(base) + idx);
+  }
+};
+struct GlobalDst {
+  float2* __restrict__ base;
+  long long so, si;
+  int valid_o, valid_c;
+  __device__ __forceinline__ void store(int o, int i, int c, float2 v) const {
+    if (o >= valid_o || c >= valid_c) return;
+    base[o * so + i * si + c] = v;
+  }
+};
+template <class Layout>
+struct SmemSrc {
+  const float2* buf;
+  __device__ __forceinline__ float2 load(int o, int i, int c) const { return buf[Layout::off(o, i, c)]; }
+};
+template <class Layout>
+struct SmemDst {
+  float2* buf;
+  __device__ __forceinline__ void store(int o, int i, int c, float2 v) const { buf[Layout::off(o, i, c)] = v; }
+};
+
+// ---- one Stockham stage over a tile -------------------------------------------------------------
+// tw points at this stage's table: tw[(j-1)*P + p] = W_{P*R}^{j*p} (conjugated for inverse).
+template <int R, int P, int N, int O, int CN, int NT, bool INV, class Src, class Dst>
+__device__ __forceinline__ void run_stage(const Src& src, const Dst& dst, const float2* __restrict__ tw, float scale,
+                                          bool do_scale) {
+  constexpr int NB = N / R;  // butterflies per transform
+  constexpr int TOTAL = O * NB * CN;
+  constexpr int ROUNDS = (TOTAL + NT - 1) / NT;
+#pragma unroll(ROUNDS <= 4 ? ROUNDS : 2)
+  for (int it = 0; it < ROUNDS; ++it) {
+    const int q = (int)threadIdx.x + it * NT;
+    if (TOTAL % NT == 0 || q < TOTAL) {
+      const int c = (CN == 1) ? 0 : q % CN;
+      const int qn = (CN == 1) ? q : q / CN;
+      const int n = (O == 1) ? qn : qn % NB;
+      const int o = (O == 1) ? 0 : qn / NB;
+      const int p = (P == 1) ? 0 : n % P;
+      const int g = (P == 1) ? n : n / P;
+      float2 x[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) x[j] = src.load(o, n + j * NB, c);
+      if constexpr (P > 1) {
+#pragma unroll
+        for (int j = 1; j < R; ++j) x[j] = cmulf(x[j], __ldg(&tw[(j - 1) * P + p]));
+      }
+      Dft<R, INV>::run(x);
+      if (do_scale) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) { x[k].x *= scale; x[k].y *= scale; }
+      }
+#pragma unroll
+      for (int k = 0; k < R; ++k) dst.store(o, g * (P * R) + p + k * P, c, x[k]);
+    }
+  }
+}
+
+// adapters: LayoutFor<Q, P> for a fixed tile shape
+template <int N>
+struct RowLayoutN {
+  template <int Q, int P>
+  using type = RowLayout<N, Q, P>;
+};
+template <int N, int CN>
+struct DenseLayoutN {
+  template <int Q, int P>
+  using type = DenseLayout<N, CN>;
+};
+// a full 2-D tile [o][i] without padding (hand-over between the two axes of a plane kernel)
+template <int NI>
+struct PlaneLayout {
+  static __device__ __forceinline__ int off(int o, int i, int) { return o * NI + i; }
+};
+
+// All stages of one axis over a tile: stage 0 from `src`, last stage to `gdst`; exchange e
+// (after stage e) goes through buffer (E0 + e) % 2. LayoutFor<Q, P> gives the exchange layout
+// after a stage with those parameters.
+template <class RL, int N, int O, int CN, int NT, bool INV, template <int, int> class LayoutFor, int E0 = 0, int S = 0,
+          class Src, class GDst>
+__device__ __forceinline__ void run_axis(const Src& src, const GDst& gdst, float2* buf0, float2* buf1,
+                                         const float2* __restrict__ tw, float scale, bool do_scale) {
+  constexpr int R = RL::r[S];
+  constexpr int P = RL::processed(S);
+  constexpr bool last = (S == RL::count - 1);
+  const float2* tws = tw + RL::tw_offset(S);
+  if constexpr (last) {
+    run_stage<R, P, N, O, CN, NT, INV>(src, gdst, tws, scale, do_scale);
+  } else {
+    using L = LayoutFor<P * R, P>;
+    float2* buf = ((E0 + S) % 2 == 0) ? buf0 : buf1;
+    run_stage<R, P, N, O, CN, NT, INV>(src, SmemDst<L>{buf}, tws, 1.f, false);
+    __syncthreads();
+    run_axis<RL, N, O, CN, NT, INV, LayoutFor, E0, S + 1>(SmemSrc<L>{buf}, gdst, buf0, buf1, tw, scale, do_scale);
+  }
+}
+
+// largest exchange buffer (in float2) a plan needs
+template <class RL, int O, template <int, int> class LayoutFor, int S = 0>
+constexpr int max_exchange_elems() {
+  if constexpr (S >= RL::count - 1) {
+    return 0;
+  } else {
+    constexpr int P = RL::processed(S);
+    constexpr int mine = LayoutFor<P * RL::r[S], P>::size(O);
+    constexpr int rest = max_exchange_elems<RL, O, LayoutFor, S + 1>();
+    return mine > rest ? mine : rest;
+  }
+}
+
+// ---- kernels ------------------------------------------------------------------------------------
+struct RowsArgs {
+  const void* in;
+  float2* out;
+  const float2* tw;
+  long long nrows;
+  float scale;
+  int do_scale;
+};
+
+// contiguous rows: tile = C consecutive transforms of length N, one tile per CTA
+template <int N, class RL, int C, int NT, bool INV, bool REAL>
+__global__ void __launch_bounds__(NT) rows_kernel(const __grid_constant__ RowsArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
+  float2* buf0 = smem_f2;
+  float2* buf1 = smem_f2 + BUF;
+  const long long row0 = (long long)blockIdx.x * C;
+  const int valid = (int)min((long long)C, a.nrows - row0);
+  const void* in = REAL ? (const void*)(reinterpret_cast<const float*>(a.in) + row0 * N)
+                        : (const void*)(reinterpret_cast<const float2*>(a.in) + row0 * N);
+  GlobalSrc<REAL> src{in, N, 1, valid, 1};
+  GlobalDst dst{a.out + row0 * N, N, 1, valid, 1};
+  run_axis<RL, N, C, 1, NT, INV, RowLayoutN<N>::template type>(src, dst, buf0, buf1, a.tw, a.scale, a.do_scale != 0);
+}
+template <int N, class RL, int C>
+constexpr size_t rows_smem_bytes() {
+  return sizeof(float2) * (size_t)max_exchange_elems<RL, C, RowLayoutN<N>::template type>() * (RL::count > 2 ? 2 : 1);
+}
+
+struct ColsArgs {
+  const void* in;
+  float2* out;
+  const float2* tw;
+  long long inner;        // element stride along the axis = number of interleaved columns
+  int tiles_per_outer;    // ceil(inner / CW)
+  float scale;
+  int do_scale;
+};
+
+// strided axis: tile = all N points of CW adjacent columns (CW*8 contiguous bytes per axis step);
+// the "transpose" the reference does with separate kernels happens in the tile addressing.
+template <int N, class RL, int CW, int NT, bool INV, bool REAL>
+__global__ void __launch_bounds__(NT) cols_kernel(const __grid_constant__ ColsArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
+  float2* buf0 = smem_f2;
+  float2* buf1 = smem_f2 + BUF;
+  const long long o = blockIdx.x / a.tiles_per_outer;
+  const long long c0 = (long long)(blockIdx.x - o * a.tiles_per_outer) * CW;
+  const long long base = o * N * a.inner + c0;
+  const int valid_c = (int)min((long long)CW, a.inner - c0);
+  const void* in = REAL ? (const void*)(reinterpret_cast<const float*>(a.in) + base)
+                        : (const void*)(reinterpret_cast<const float2*>(a.in) + base);
+  GlobalSrc<REAL> src{in, 0, a.inner, 1, valid_c};
+  GlobalDst dst{a.out + base, 0, a.inner, 1, valid_c};
+  run_axis<RL, N, 1, CW, NT, INV, DenseLayoutN<N, CW>::template type>(src, dst, buf0, buf1, a.tw, a.scale,
+                                                                      a.do_scale != 0);
+}
+template <int N, class RL, int CW>
+constexpr size_t cols_smem_bytes() {
+  return sizeof(float2) * (size_t)max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>() *
+         (RL::count > 2 ? 2 : 1);
+}
+
+}  // namespace b200fft

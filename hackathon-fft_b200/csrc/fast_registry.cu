@@ -1,0 +1,295 @@
+// Registry of compile-time kernel variants (fast.cuh) and the passes that launch them.
+//
+// A variant is (axis length N, super-stage list, tile size, threads). The planner picks, for
+// an axis, the first registered variant whose super-stages can be formed by grouping the
+// axis's ordered base list (the reference's stage list, _utils.mojo:163-221): e.g. user
+// bases [2] on 128 -> stages [2]x7 -> fused as (16)(8). Bases that cannot be grouped into any
+// registered variant (say [32,4] with only (16,8) registered) run on the generic kernel.
+// B200FFT_PREFER="substr[,substr...]" moves matching variant names to the front (tuning aid).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "fast.cuh"
+#include "plan.hpp"
+
+namespace b200fft {
+namespace {
+
+enum Kind { ROWS = 0, COLS = 1 };
+
+struct Variant {
+  std::string name;
+  Kind kind;
+  int n;
+  std::vector<int> radices;
+  int tile, threads;
+  size_t smem;
+  // inv, real_in
+  void (*launch_rows)(bool, bool, const RowsArgs&, unsigned, size_t, cudaStream_t);
+  void (*launch_cols)(bool, bool, const ColsArgs&, unsigned, size_t, cudaStream_t);
+  cudaError_t (*prepare)(size_t);
+};
+
+std::vector<Variant>& registry() {
+  static std::vector<Variant> r;
+  return r;
+}
+
+template <int N, class RL, int C, int NT>
+struct RowsV {
+  static void launch(bool inv, bool real, const RowsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    if (!inv && !real) rows_kernel<N, RL, C, NT, false, false><<<grid, NT, smem, st>>>(a);
+    else if (!inv && real) rows_kernel<N, RL, C, NT, false, true><<<grid, NT, smem, st>>>(a);
+    else if (inv && !real) rows_kernel<N, RL, C, NT, true, false><<<grid, NT, smem, st>>>(a);
+    else rows_kernel<N, RL, C, NT, true, true><<<grid, NT, smem, st>>>(a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+    if ((e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+    if ((e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+    return cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+};
+
+template <int N, class RL, int CW, int NT>
+struct ColsV {
+  static void launch(bool inv, bool real, const ColsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    if (!inv && !real) cols_kernel<N, RL, CW, NT, false, false><<<grid, NT, smem, st>>>(a);
+    else if (!inv && real) cols_kernel<N, RL, CW, NT, false, true><<<grid, NT, smem, st>>>(a);
+    else if (inv && !real) cols_kernel<N, RL, CW, NT, true, false><<<grid, NT, smem, st>>>(a);
+    else cols_kernel<N, RL, CW, NT, true, true><<<grid, NT, smem, st>>>(a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+    if ((e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+    if ((e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+    return cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+};
+
+template <class RL>
+std::vector<int> radix_vec() {
+  return std::vector<int>(RL::r, RL::r + RL::count);
+}
+std::string radix_name(const std::vector<int>& r) {
+  std::string s;
+  for (int v : r) s += (s.empty() ? "" : "x") + std::to_string(v);
+  return s;
+}
+
+template <int N, int C, int NT, int... Rs>
+void reg_rows() {
+  using RL = Radices<Rs...>;
+  static_assert(RL::product() == N, "radices must multiply to N");
+  Variant v;
+  v.kind = ROWS; v.n = N; v.radices = radix_vec<RL>(); v.tile = C; v.threads = NT;
+  v.smem = rows_smem_bytes<N, RL, C>();
+  v.name = "rows" + std::to_string(N) + "_" + radix_name(v.radices) + "_c" + std::to_string(C) + "_t" + std::to_string(NT);
+  v.launch_rows = &RowsV<N, RL, C, NT>::launch;
+  v.launch_cols = nullptr;
+  v.prepare = &RowsV<N, RL, C, NT>::prepare;
+  registry().push_back(v);
+}
+template <int N, int CW, int NT, int... Rs>
+void reg_cols() {
+  using RL = Radices<Rs...>;
+  static_assert(RL::product() == N, "radices must multiply to N");
+  Variant v;
+  v.kind = COLS; v.n = N; v.radices = radix_vec<RL>(); v.tile = CW; v.threads = NT;
+  v.smem = cols_smem_bytes<N, RL, CW>();
+  v.name = "cols" + std::to_string(N) + "_" + radix_name(v.radices) + "_w" + std::to_string(CW) + "_t" + std::to_string(NT);
+  v.launch_rows = nullptr;
+  v.launch_cols = &ColsV<N, RL, CW, NT>::launch;
+  v.prepare = &ColsV<N, RL, CW, NT>::prepare;
+  registry().push_back(v);
+}
+
+void register_all() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  // ---- contiguous rows: <N, rows per CTA, threads, super-stages...>
+  reg_rows<128, 32, 256, 16, 8>();
+  reg_rows<128, 32, 256, 8, 16>();
+  reg_rows<1024, 4, 256, 16, 16, 4>();
+  reg_rows<1024, 8, 256, 32, 32>();
+  reg_rows<93, 64, 192, 31, 3>();
+  reg_rows<64, 32, 256, 8, 8>();
+  reg_rows<256, 16, 256, 16, 16>();
+  reg_rows<512, 8, 256, 8, 8, 8>();
+  reg_rows<480, 8, 192, 10, 8, 6>();
+  reg_rows<640, 4, 256, 10, 8, 8>();
+  // ---- strided axes: <N, columns per CTA, threads, super-stages...>
+  reg_cols<64, 16, 128, 8, 8>();
+  reg_cols<128, 16, 128, 16, 8>();
+  reg_cols<256, 16, 256, 16, 16>();
+  reg_cols<512, 8, 256, 8, 8, 8>();
+  reg_cols<640, 8, 160, 10, 8, 8>();
+  reg_cols<480, 8, 192, 10, 8, 6>();
+}
+
+// can `target` (super-stage radices) be formed by partitioning `ordered` (the user's stage
+// list) into groups with exactly those products?
+bool can_group(std::vector<uint32_t> ordered, std::vector<int> target) {
+  if (target.empty()) return ordered.empty();
+  const int want = target.back();
+  target.pop_back();
+  // choose a sub-multiset of `ordered` with product `want`
+  const size_t n = ordered.size();
+  if (n > 24) return false;
+  std::function<bool(size_t, int, std::vector<uint32_t>&)> rec = [&](size_t i, int prod, std::vector<uint32_t>& rest) {
+    if (prod == want) {
+      std::vector<uint32_t> remaining(rest);
+      remaining.insert(remaining.end(), ordered.begin() + i, ordered.end());
+      return can_group(remaining, target);
+    }
+    if (i >= n || prod > want) return false;
+    // take ordered[i]
+    if (want % (prod * (int)ordered[i]) == 0) {
+      if (rec(i + 1, prod * (int)ordered[i], rest)) return true;
+    }
+    // skip ordered[i] (and equal values, to avoid re-trying the same choice)
+    size_t k = i;
+    while (k < n && ordered[k] == ordered[i]) { rest.push_back(ordered[k]); ++k; }
+    const bool ok = rec(k, prod, rest);
+    for (size_t t = i; t < k; ++t) rest.pop_back();
+    return ok;
+  };
+  std::vector<uint32_t> rest;
+  return rec(0, 1, rest);
+}
+
+// per-stage twiddle table: stage s >= 1 holds tw[(j-1)*P + p] = W_{P*R}^{j*p}
+std::vector<float2> build_twiddles(const std::vector<int>& radices, bool inverse) {
+  std::vector<float2> t;
+  long long P = 1;
+  for (size_t s = 0; s < radices.size(); ++s) {
+    const int R = radices[s];
+    if (s > 0) {
+      const long long Q = P * R;
+      for (int j = 1; j < R; ++j)
+        for (long long p = 0; p < P; ++p) {
+          const double th = 2.0 * M_PI * (double)((j * p) % Q) / (double)Q;
+          t.push_back(make_float2((float)std::cos(th), (float)((inverse ? 1.0 : -1.0) * std::sin(th))));
+        }
+    }
+    P *= R;
+  }
+  if (t.empty()) t.push_back(make_float2(1.f, 0.f));
+  return t;
+}
+
+struct FastPass : Pass {
+  const Variant* v = nullptr;
+  AxisView view;
+  bool inverse = false, real_in = false, do_scale = false;
+  float scale = 1.f;
+  float2* d_tw = nullptr;
+  std::string text;
+
+  int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) override {
+    if (v->kind == ROWS) {
+      RowsArgs a;
+      a.in = src;
+      a.out = reinterpret_cast<float2*>(dst);
+      a.tw = d_tw;
+      a.nrows = nbatch * view.outer_per_batch;
+      a.scale = scale;
+      a.do_scale = do_scale;
+      const long long grid = (a.nrows + v->tile - 1) / v->tile;
+      if (grid <= 0) return B200FFT_OK;
+      if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many row tiles");
+      v->launch_rows(inverse, real_in, a, (unsigned)grid, v->smem, stream);
+    } else {
+      ColsArgs a;
+      a.in = src;
+      a.out = reinterpret_cast<float2*>(dst);
+      a.tw = d_tw;
+      a.inner = view.inner;
+      a.tiles_per_outer = (int)((view.inner + v->tile - 1) / v->tile);
+      a.scale = scale;
+      a.do_scale = do_scale;
+      const long long grid = nbatch * view.outer_per_batch * a.tiles_per_outer;
+      if (grid <= 0) return B200FFT_OK;
+      if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many column tiles");
+      v->launch_cols(inverse, real_in, a, (unsigned)grid, v->smem, stream);
+    }
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200FFT_OK;
+  }
+  std::string describe() const override { return text; }
+};
+
+}  // namespace
+
+std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
+                                     bool scale_inverse) {
+  register_all();
+  const Problem& p = plan.prob;
+  if (p.desc.out_dtype != B200FFT_F32 || src.dtype != B200FFT_F32) return nullptr;
+  if (view.n > 0x7fffffff) return nullptr;
+  const Kind kind = view.inner == 1 ? ROWS : COLS;
+  const AxisSpec& ax = p.axes[axis];
+
+  std::vector<const Variant*> cands;
+  for (const Variant& v : registry())
+    if (v.kind == kind && v.n == (int)view.n && can_group(ax.ordered, v.radices)) cands.push_back(&v);
+  if (cands.empty()) return nullptr;
+  if (const char* pref = getenv("B200FFT_PREFER")) {
+    std::string s(pref);
+    size_t pos = 0;
+    std::vector<std::string> keys;
+    while (pos <= s.size()) {
+      size_t e = s.find(',', pos);
+      if (e == std::string::npos) e = s.size();
+      if (e > pos) keys.push_back(s.substr(pos, e - pos));
+      pos = e + 1;
+    }
+    std::stable_sort(cands.begin(), cands.end(), [&](const Variant* a, const Variant* b) {
+      auto rank = [&](const Variant* v) {
+        for (size_t i = 0; i < keys.size(); ++i)
+          if (v->name.find(keys[i]) != std::string::npos) return (int)i;
+        return (int)keys.size();
+      };
+      return rank(a) < rank(b);
+    });
+  }
+  const Variant* v = cands[0];
+  if (v->prepare(v->smem) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  auto pass = std::make_unique<FastPass>();
+  pass->v = v;
+  pass->view = view;
+  pass->inverse = p.desc.inverse != 0;
+  pass->real_in = src.comps == 1;
+  pass->do_scale = scale_inverse;
+  pass->scale = scale_inverse ? (float)(1.0 / (double)view.n) : 1.f;
+  std::vector<float2> tw = build_twiddles(v->radices, pass->inverse);
+  if (cudaMalloc(&pass->d_tw, tw.size() * sizeof(float2)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(pass->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  plan.owned_device.push_back(pass->d_tw);
+  std::string stages;
+  for (uint32_t r : ax.ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
+  char buf[320];
+  snprintf(buf, sizeof buf, "axis %d: %s n=%lld inner=%lld smem=%zuB user stages=[%s] fused as (%s)%s", axis,
+           v->name.c_str(), (long long)view.n, (long long)view.inner, v->smem, stages.c_str(),
+           radix_name(v->radices).c_str(), pass->real_in ? " real-in" : "");
+  pass->text = buf;
+  return pass;
+}
+
+}  // namespace b200fft

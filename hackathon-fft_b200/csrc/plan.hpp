@@ -73,5 +73,8 @@ namespace b200fft {
 // kernel families (each returns nullptr when it does not cover the request)
 std::unique_ptr<Pass> make_generic_pass(const b200fft_plan& plan, int axis, const AxisView& view,
                                         const IoSpec& src, bool scale_inverse);
+// compile-time kernels (fast_registry.cu); allocates its stage twiddle table into plan.owned_device
+std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
+                                     bool scale_inverse);
 
 }  // namespace b200fft
