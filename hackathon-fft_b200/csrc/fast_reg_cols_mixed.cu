@@ -1,0 +1,12 @@
+// Strided-axis variants, mixed-radix lengths: <N, columns per CTA, threads, FULL, super-stages...>
+#include "fast_registry.hpp"
+namespace b200fft {
+void register_cols_mixed() {
+  reg_cols<640, 16, 320, true, 32, 20>();
+  reg_cols<640, 8, 160, true, 10, 8, 8>();
+  reg_cols<640, 8, 160, false, 32, 20>();
+  reg_cols<640, 16, 640, false, 32, 20>();
+  reg_cols<480, 16, 320, true, 24, 20>();
+  reg_cols<480, 8, 192, true, 10, 8, 6>();
+}
+}  // namespace b200fft

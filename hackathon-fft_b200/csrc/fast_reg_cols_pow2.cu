@@ -1,0 +1,14 @@
+// Strided-axis variants, power-of-two lengths: <N, columns per CTA, threads, FULL, super-stages...>
+#include "fast_registry.hpp"
+namespace b200fft {
+void register_cols_pow2() {
+  reg_cols<64, 16, 128, true, 8, 8>();
+  reg_cols<128, 16, 128, true, 16, 8>();
+  reg_cols<256, 16, 256, true, 16, 16>();
+  reg_cols<512, 16, 256, true, 32, 16>();
+  reg_cols<512, 8, 256, true, 8, 8, 8>();
+  reg_cols<512, 8, 128, false, 32, 16>();
+  reg_cols<512, 16, 512, false, 32, 16>();
+  reg_cols<1024, 8, 256, true, 32, 32>();
+}
+}  // namespace b200fft

@@ -1,0 +1,15 @@
+// Contiguous-row variants, mixed-radix lengths: <N, rows per CTA, threads, FULL, super-stages...>
+#include "fast_registry.hpp"
+namespace b200fft {
+void register_rows_mixed() {
+  reg_rows<93, 32, 96, true, 31, 3>();
+  reg_rows<93, 16, 48, false, 31, 3>();
+  reg_rows<93, 64, 96, false, 31, 3>();
+  reg_rows<480, 8, 192, true, 24, 20>();
+  reg_rows<480, 8, 192, true, 10, 8, 6>();
+  reg_rows<480, 16, 384, false, 24, 20>();
+  reg_rows<480, 8, 256, false, 30, 16>();
+  reg_rows<640, 8, 256, true, 32, 20>();
+  reg_rows<640, 4, 256, true, 10, 8, 8>();
+}
+}  // namespace b200fft

@@ -16,127 +16,30 @@
 #include <string>
 #include <vector>
 
-#include "fast.cuh"
+#include "fast_registry.hpp"
 #include "plan.hpp"
 
 namespace b200fft {
-namespace {
-
-enum Kind { ROWS = 0, COLS = 1 };
-
-struct Variant {
-  std::string name;
-  Kind kind;
-  int n;
-  std::vector<int> radices;
-  int tile, threads;
-  size_t smem;
-  // inv, real_in
-  void (*launch_rows)(bool, bool, const RowsArgs&, unsigned, size_t, cudaStream_t);
-  void (*launch_cols)(bool, bool, const ColsArgs&, unsigned, size_t, cudaStream_t);
-  cudaError_t (*prepare)(size_t);
-};
 
 std::vector<Variant>& registry() {
   static std::vector<Variant> r;
   return r;
 }
+void register_rows_pow2();
+void register_rows_mixed();
+void register_cols_pow2();
+void register_cols_mixed();
 
-template <int N, class RL, int C, int NT>
-struct RowsV {
-  static void launch(bool inv, bool real, const RowsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
-    if (!inv && !real) rows_kernel<N, RL, C, NT, false, false><<<grid, NT, smem, st>>>(a);
-    else if (!inv && real) rows_kernel<N, RL, C, NT, false, true><<<grid, NT, smem, st>>>(a);
-    else if (inv && !real) rows_kernel<N, RL, C, NT, true, false><<<grid, NT, smem, st>>>(a);
-    else rows_kernel<N, RL, C, NT, true, true><<<grid, NT, smem, st>>>(a);
-  }
-  static cudaError_t prepare(size_t smem) {
-    if (smem <= 48 * 1024) return cudaSuccess;
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    if ((e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    if ((e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    return cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-};
-
-template <int N, class RL, int CW, int NT>
-struct ColsV {
-  static void launch(bool inv, bool real, const ColsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
-    if (!inv && !real) cols_kernel<N, RL, CW, NT, false, false><<<grid, NT, smem, st>>>(a);
-    else if (!inv && real) cols_kernel<N, RL, CW, NT, false, true><<<grid, NT, smem, st>>>(a);
-    else if (inv && !real) cols_kernel<N, RL, CW, NT, true, false><<<grid, NT, smem, st>>>(a);
-    else cols_kernel<N, RL, CW, NT, true, true><<<grid, NT, smem, st>>>(a);
-  }
-  static cudaError_t prepare(size_t smem) {
-    if (smem <= 48 * 1024) return cudaSuccess;
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    if ((e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    if ((e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    return cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-};
-
-template <class RL>
-std::vector<int> radix_vec() {
-  return std::vector<int>(RL::r, RL::r + RL::count);
-}
-std::string radix_name(const std::vector<int>& r) {
-  std::string s;
-  for (int v : r) s += (s.empty() ? "" : "x") + std::to_string(v);
-  return s;
-}
-
-template <int N, int C, int NT, int... Rs>
-void reg_rows() {
-  using RL = Radices<Rs...>;
-  static_assert(RL::product() == N, "radices must multiply to N");
-  Variant v;
-  v.kind = ROWS; v.n = N; v.radices = radix_vec<RL>(); v.tile = C; v.threads = NT;
-  v.smem = rows_smem_bytes<N, RL, C>();
-  v.name = "rows" + std::to_string(N) + "_" + radix_name(v.radices) + "_c" + std::to_string(C) + "_t" + std::to_string(NT);
-  v.launch_rows = &RowsV<N, RL, C, NT>::launch;
-  v.launch_cols = nullptr;
-  v.prepare = &RowsV<N, RL, C, NT>::prepare;
-  registry().push_back(v);
-}
-template <int N, int CW, int NT, int... Rs>
-void reg_cols() {
-  using RL = Radices<Rs...>;
-  static_assert(RL::product() == N, "radices must multiply to N");
-  Variant v;
-  v.kind = COLS; v.n = N; v.radices = radix_vec<RL>(); v.tile = CW; v.threads = NT;
-  v.smem = cols_smem_bytes<N, RL, CW>();
-  v.name = "cols" + std::to_string(N) + "_" + radix_name(v.radices) + "_w" + std::to_string(CW) + "_t" + std::to_string(NT);
-  v.launch_rows = nullptr;
-  v.launch_cols = &ColsV<N, RL, CW, NT>::launch;
-  v.prepare = &ColsV<N, RL, CW, NT>::prepare;
-  registry().push_back(v);
-}
+namespace {
 
 void register_all() {
   static bool done = false;
   if (done) return;
   done = true;
-  // ---- contiguous rows: <N, rows per CTA, threads, super-stages...>
-  reg_rows<128, 32, 256, 16, 8>();
-  reg_rows<128, 32, 256, 8, 16>();
-  reg_rows<1024, 4, 256, 16, 16, 4>();
-  reg_rows<1024, 8, 256, 32, 32>();
-  reg_rows<93, 64, 192, 31, 3>();
-  reg_rows<64, 32, 256, 8, 8>();
-  reg_rows<256, 16, 256, 16, 16>();
-  reg_rows<512, 8, 256, 8, 8, 8>();
-  reg_rows<480, 8, 192, 10, 8, 6>();
-  reg_rows<640, 4, 256, 10, 8, 8>();
-  // ---- strided axes: <N, columns per CTA, threads, super-stages...>
-  reg_cols<64, 16, 128, 8, 8>();
-  reg_cols<128, 16, 128, 16, 8>();
-  reg_cols<256, 16, 256, 16, 16>();
-  reg_cols<512, 8, 256, 8, 8, 8>();
-  reg_cols<640, 8, 160, 10, 8, 8>();
-  reg_cols<480, 8, 192, 10, 8, 6>();
+  register_rows_pow2();
+  register_rows_mixed();
+  register_cols_pow2();
+  register_cols_mixed();
 }
 
 // can `target` (super-stage radices) be formed by partitioning `ordered` (the user's stage
@@ -245,7 +148,9 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
 
   std::vector<const Variant*> cands;
   for (const Variant& v : registry())
-    if (v.kind == kind && v.n == (int)view.n && can_group(ax.ordered, v.radices)) cands.push_back(&v);
+    if (v.kind == kind && v.n == (int)view.n && (v.full || (!p.desc.inverse && src.comps == 2)) &&
+        can_group(ax.ordered, v.radices))
+      cands.push_back(&v);
   if (cands.empty()) return nullptr;
   if (const char* pref = getenv("B200FFT_PREFER")) {
     std::string s(pref);

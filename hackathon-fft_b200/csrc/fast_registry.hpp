@@ -1,0 +1,119 @@
+// Variant table shared by the registration units (fast_reg_*.cu) and the pass factory.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "fast.cuh"
+
+namespace b200fft {
+
+enum Kind { ROWS = 0, COLS = 1 };
+
+struct Variant {
+  std::string name;
+  Kind kind;
+  int n;
+  std::vector<int> radices;
+  int tile, threads;
+  size_t smem;
+  // inv, real_in
+  void (*launch_rows)(bool, bool, const RowsArgs&, unsigned, size_t, cudaStream_t);
+  void (*launch_cols)(bool, bool, const ColsArgs&, unsigned, size_t, cudaStream_t);
+  cudaError_t (*prepare)(size_t);
+  bool full;  // has inverse and real-input instantiations
+};
+
+std::vector<Variant>& registry();
+
+
+// FULL variants instantiate forward/inverse x complex/real-input; tuning candidates only
+// forward complex (they are skipped for other requests).
+template <int N, class RL, int C, int NT, bool FULL>
+struct RowsV {
+  static void launch(bool inv, bool real, const RowsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    if constexpr (FULL) {
+      if (!inv && real) return (void)rows_kernel<N, RL, C, NT, false, true><<<grid, NT, smem, st>>>(a);
+      if (inv && !real) return (void)rows_kernel<N, RL, C, NT, true, false><<<grid, NT, smem, st>>>(a);
+      if (inv && real) return (void)rows_kernel<N, RL, C, NT, true, true><<<grid, NT, smem, st>>>(a);
+    }
+    rows_kernel<N, RL, C, NT, false, false><<<grid, NT, smem, st>>>(a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, false>, attr, (int)smem);
+    if constexpr (FULL) {
+      if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, true>, attr, (int)smem);
+      if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, false>, attr, (int)smem);
+      if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, true>, attr, (int)smem);
+    }
+    return e;
+  }
+};
+
+template <int N, class RL, int CW, int NT, bool FULL>
+struct ColsV {
+  static void launch(bool inv, bool real, const ColsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    if constexpr (FULL) {
+      if (!inv && real) return (void)cols_kernel<N, RL, CW, NT, false, true><<<grid, NT, smem, st>>>(a);
+      if (inv && !real) return (void)cols_kernel<N, RL, CW, NT, true, false><<<grid, NT, smem, st>>>(a);
+      if (inv && real) return (void)cols_kernel<N, RL, CW, NT, true, true><<<grid, NT, smem, st>>>(a);
+    }
+    cols_kernel<N, RL, CW, NT, false, false><<<grid, NT, smem, st>>>(a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, false, false>, attr, (int)smem);
+    if constexpr (FULL) {
+      if (!e) e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, false, true>, attr, (int)smem);
+      if (!e) e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, true, false>, attr, (int)smem);
+      if (!e) e = cudaFuncSetAttribute(cols_kernel<N, RL, CW, NT, true, true>, attr, (int)smem);
+    }
+    return e;
+  }
+};
+
+template <class RL>
+std::vector<int> radix_vec() {
+  return std::vector<int>(RL::r, RL::r + RL::count);
+}
+inline std::string radix_name(const std::vector<int>& r) {
+  std::string s;
+  for (int v : r) s += (s.empty() ? "" : "x") + std::to_string(v);
+  return s;
+}
+
+template <int N, int C, int NT, bool FULL, int... Rs>
+void reg_rows() {
+  using RL = Radices<Rs...>;
+  static_assert(RL::product() == N, "radices must multiply to N");
+  Variant v;
+  v.kind = ROWS; v.n = N; v.radices = radix_vec<RL>(); v.tile = C; v.threads = NT;
+  v.smem = rows_smem_bytes<N, RL, C>();
+  v.name = "rows" + std::to_string(N) + "_" + radix_name(v.radices) + "_c" + std::to_string(C) + "_t" + std::to_string(NT);
+  v.launch_rows = &RowsV<N, RL, C, NT, FULL>::launch;
+  v.launch_cols = nullptr;
+  v.prepare = &RowsV<N, RL, C, NT, FULL>::prepare;
+  v.full = FULL;
+  registry().push_back(v);
+}
+template <int N, int CW, int NT, bool FULL, int... Rs>
+void reg_cols() {
+  using RL = Radices<Rs...>;
+  static_assert(RL::product() == N, "radices must multiply to N");
+  Variant v;
+  v.kind = COLS; v.n = N; v.radices = radix_vec<RL>(); v.tile = CW; v.threads = NT;
+  v.smem = cols_smem_bytes<N, RL, CW>();
+  v.name = "cols" + std::to_string(N) + "_" + radix_name(v.radices) + "_w" + std::to_string(CW) + "_t" + std::to_string(NT);
+  v.launch_rows = nullptr;
+  v.launch_cols = &ColsV<N, RL, CW, NT, FULL>::launch;
+  v.prepare = &ColsV<N, RL, CW, NT, FULL>::prepare;
+  v.full = FULL;
+  registry().push_back(v);
+}
+
+
+}  // namespace b200fft
