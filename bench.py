@@ -45,6 +45,7 @@ SHAPES = [
     ("1d_500000x93", (500000, 93), False),
     ("2d_100x640x480", (100, 640, 480), False),
     ("2d_100x640x480_r2c_full", (100, 640, 480), True),
+    ("2d_100x640x480_r2c_half", (100, 640, 480), "half"),
     ("3d_100x64x64x64", (100, 64, 64, 64), False),
     ("3d_10x128x128x128", (10, 128, 128, 128), False),
     ("3d_1x256x256x256", (1, 256, 256, 256), False),
@@ -241,21 +242,24 @@ def run_reference_arm(args):
 def bench_shape(name, shape, real_in, torch, b200fft, steps, warmup, peak):
     """ours vs cuFFT on one shape, same buffers, same stream, CUDA events."""
     comps = 1 if real_in else 2
-    row = {"name": name, "shape": list(shape), "real_in": real_in}
+    half = real_in == "half"
+    row = {"name": name, "shape": list(shape), "real_in": bool(real_in), "half_spectrum": half}
     try:
         g = torch.Generator(device="cuda").manual_seed(1234)
         x = torch.randn(tuple(shape) + (comps,), generator=g, device="cuda", dtype=torch.float32)
-        out = torch.empty(tuple(shape) + (2,), device="cuda", dtype=torch.float32)
-        plan = b200fft.plan_fft("float32", "float32", x.shape, out.shape)
+        oshape = tuple(shape[:-1]) + (shape[-1] // 2 + 1, 2) if half else tuple(shape) + (2,)
+        out = torch.empty(oshape, device="cuda", dtype=torch.float32)
+        plan = b200fft.plan_fft("float32", "float32", x.shape, out.shape,
+                                real_mode=b200fft.REAL_HALF if half else b200fft.REAL_FULL)
         stream = torch.cuda.current_stream().cuda_stream
         ms = time_gpu(lambda: plan.exec(out, x, stream), warmup, steps, torch)
-        ab = algorithmic_bytes(shape, real_in)
+        ab = algorithmic_bytes(shape, real_in) if not half else int(np.prod(shape)) * 4 + int(np.prod(oshape)) * 4
         row.update({"ms": ms, "gflops": flops_c2c(shape) * (0.5 if real_in else 1.0) / ms / 1e6,
                     "gbs": ab / ms / 1e6, "hbm_frac": ab / ms / 1e6 / peak, "launches": plan.launches,
                     "kernels": plan.describe().strip().split("\n")})
         # parity on one batch item against numpy f64
         ref_in = x[0].double().cpu().numpy()
-        want = np.fft.fftn(ref_in[..., 0] + (1j * ref_in[..., 1] if comps == 2 else 0))
+        want = np.fft.rfftn(ref_in[..., 0]) if half else np.fft.fftn(ref_in[..., 0] + (1j * ref_in[..., 1] if comps == 2 else 0))
         got = out[0].double().cpu().numpy()
         got = got[..., 0] + 1j * got[..., 1]
         row["rel_l2_vs_numpy_f64"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
@@ -267,8 +271,9 @@ def bench_shape(name, shape, real_in, torch, b200fft, steps, warmup, peak):
                 cout = torch.empty(half, device="cuda", dtype=torch.float32)
             else:
                 cout = torch.empty_like(out)
-            cf = CuFFT(shape, r2c=real_in)
+            cf = CuFFT(shape, r2c=bool(real_in))
             cms = time_gpu(lambda: cf.exec(x, cout, stream), warmup, steps, torch)
+            row["cufft_note"] = "cuFFT R2C writes the half spectrum" if real_in else ""
             cf.destroy()
             row.update({"cufft_ms": cms, "ours_over_cufft": ms / cms})
             del cout

@@ -62,37 +62,99 @@ AxisView view_of(const Problem& p, int axis) {
   return v;
 }
 
+std::unique_ptr<Pass> make_pass(b200fft_plan* plan, int axis, const AxisView& view, const IoSpec& src, HalfMode half) {
+  const Problem& p = plan->prob;
+  std::unique_ptr<Pass> pass;
+  if (!(p.desc.flags & B200FFT_FLAG_FORCE_GENERIC)) pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+  if (!pass) pass = make_generic_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+  return pass;
+}
+
+std::string stage_text(const Problem& p, int axis) {
+  std::string radices;
+  for (uint32_t r : p.axes[axis].ordered) radices += (radices.empty() ? "" : ",") + std::to_string(r);
+  return radices;
+}
+
 // Kernel selection. Axes run right to left like the reference (_ndim_fft_gpu.mojo:635-642);
 // the first pass reads the user's input (cast / real -> complex), the rest run in
 // place on the output. `dry` builds only the description.
+//
+// B200FFT_REAL_HALF: forward = R2C rows pass on the last axis (input -> output), then the
+// other axes as strided passes over the (.., n/2+1) half spectrum in place. Inverse = the
+// other axes first (input -> workspace, in place on the workspace), then the C2R rows pass
+// (workspace -> output); rank 1 needs no workspace.
 int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
   const Problem& p = plan->prob;
-  if (p.half) return fail(B200FFT_ERR_UNSUPPORTED, "REAL_HALF is not built yet");
-  bool first = true;
-  for (int axis = p.rank - 1; axis >= 0; --axis) {
-    if (!p.axes[axis].transformed) continue;
-    const AxisView view = view_of(p, axis);
-    IoSpec src;
-    if (first) { src.dtype = p.desc.in_dtype; src.comps = p.desc.in_components; }
-    else { src.dtype = p.desc.out_dtype; src.comps = 2; }
+  const int last = p.rank - 1;
+  const IoSpec in_spec{p.desc.in_dtype, p.desc.in_components};
+  const IoSpec work_spec{p.desc.out_dtype, 2};
+  auto add = [&](int axis, AxisView view, IoSpec src, HalfMode half, BufSel ssel, BufSel dsel) -> int {
     if (dry) {
-      std::string radices;
-      for (uint32_t r : p.axes[axis].ordered) radices += (radices.empty() ? "" : ",") + std::to_string(r);
       char buf[256];
-      snprintf(buf, sizeof buf, "axis %d: n=%lld inner=%lld stages=[%s]%s\n", axis, (long long)view.n,
-               (long long)view.inner, radices.c_str(), first ? " (reads input)" : " (in place)");
+      snprintf(buf, sizeof buf, "axis %d: n=%lld inner=%lld stages=[%s]%s%s\n", axis, (long long)view.n,
+               (long long)view.inner, stage_text(p, axis).c_str(),
+               half == HALF_R2C ? " r2c" : half == HALF_C2R ? " c2r" : "",
+               ssel == BUF_INPUT ? " (reads input)" : " (in place)");
       *text += buf;
-    } else {
-      std::unique_ptr<Pass> pass;
-      if (!(p.desc.flags & B200FFT_FLAG_FORCE_GENERIC)) pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0);
-      if (!pass) pass = make_generic_pass(*plan, axis, view, src, p.desc.inverse != 0);
-      if (!pass) return B200FFT_ERR_UNSUPPORTED;
-      pass->reads_input = first;
-      plan->passes.push_back(std::move(pass));
+      return B200FFT_OK;
     }
-    first = false;
+    std::unique_ptr<Pass> pass = make_pass(plan, axis, view, src, half);
+    if (!pass) return B200FFT_ERR_UNSUPPORTED;
+    pass->src_sel = ssel;
+    pass->dst_sel = dsel;
+    plan->passes.push_back(std::move(pass));
+    return B200FFT_OK;
+  };
+
+  if (!p.half) {
+    bool first = true;
+    for (int axis = last; axis >= 0; --axis) {
+      if (!p.axes[axis].transformed) continue;
+      int rc = add(axis, view_of(p, axis), first ? in_spec : work_spec, HALF_NONE, first ? BUF_INPUT : BUF_OUTPUT,
+                   BUF_OUTPUT);
+      if (rc) return rc;
+      first = false;
+    }
+    return B200FFT_OK;
   }
-  return B200FFT_OK;
+
+  // ---- half spectrum: strided passes see the last axis as n/2+1 complex bins
+  const int64_t hb = p.axes[last].n / 2 + 1;
+  auto half_view = [&](int axis) {
+    AxisView v;
+    v.n = p.axes[axis].n;
+    for (int a = 0; a < axis; ++a) v.outer_per_batch *= p.axes[a].n;
+    for (int a = axis + 1; a < last; ++a) v.inner *= p.axes[a].n;
+    v.inner *= hb;
+    return v;
+  };
+  AxisView rows = view_of(p, last);  // outer_per_batch = prod(dims[:-1]), n = real length
+  if (!p.desc.inverse) {
+    int rc = add(last, rows, in_spec, HALF_R2C, BUF_INPUT, BUF_OUTPUT);
+    if (rc) return rc;
+    for (int axis = last - 1; axis >= 0; --axis) {
+      if (!p.axes[axis].transformed) continue;
+      if ((rc = add(axis, half_view(axis), work_spec, HALF_NONE, BUF_OUTPUT, BUF_OUTPUT))) return rc;
+    }
+    return B200FFT_OK;
+  }
+  bool any = false;
+  for (int axis = last - 1; axis >= 0; --axis) {
+    if (!p.axes[axis].transformed) continue;
+    int rc = add(axis, half_view(axis), any ? work_spec : in_spec, HALF_NONE, any ? BUF_WORK : BUF_INPUT, BUF_WORK);
+    if (rc) return rc;
+    any = true;
+  }
+  if (any && !dry) {
+    plan->work_stride = (size_t)(rows.outer_per_batch * hb) * 2 * p.out_elem;
+    plan->workspace_bytes = plan->work_stride * (size_t)p.batch;
+    if (cudaMalloc(&plan->workspace, plan->workspace_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(B200FFT_ERR_ALLOC, "cannot allocate %zu B of C2R workspace", plan->workspace_bytes);
+    }
+  }
+  return add(last, rows, any ? work_spec : in_spec, HALF_C2R, any ? BUF_WORK : BUF_INPUT, BUF_OUTPUT);
 }
 
 int copy_bases(const std::vector<uint32_t>& v, uint32_t* out, int cap) {
@@ -203,7 +265,9 @@ int b200fft_plan_destroy(b200fft_plan* plan) {
   return B200FFT_OK;
 }
 
-static int run_passes(b200fft_plan* plan, void* d_out, const void* d_in, int64_t nbatch, cudaStream_t st) {
+// work_batch0: first batch item of this call inside the plan-wide workspace (exec_host chunks)
+static int run_passes(b200fft_plan* plan, void* d_out, const void* d_in, int64_t nbatch, cudaStream_t st,
+                      int64_t work_batch0 = 0) {
   const Problem& p = plan->prob;
   const size_t in_stride = (size_t)p.in_scalars_per_batch * p.in_elem;
   const size_t out_stride = (size_t)p.out_scalars_per_batch * p.out_elem;
@@ -212,8 +276,11 @@ static int run_passes(b200fft_plan* plan, void* d_out, const void* d_in, int64_t
     const int64_t nb = std::min<int64_t>(chunk, nbatch - b0);
     char* out_b = (char*)d_out + (size_t)b0 * out_stride;
     const char* in_b = (const char*)d_in + (size_t)b0 * in_stride;
+    char* work_b = (char*)plan->workspace + (size_t)(b0 + work_batch0) * plan->work_stride;
     for (auto& pass : plan->passes) {
-      int rc = pass->launch(pass->reads_input ? (const void*)in_b : (const void*)out_b, out_b, nb, st);
+      const void* src = pass->src_sel == BUF_INPUT ? (const void*)in_b : pass->src_sel == BUF_WORK ? (const void*)work_b : (const void*)out_b;
+      void* dst = pass->dst_sel == BUF_WORK ? (void*)work_b : (void*)out_b;
+      int rc = pass->launch(src, dst, nb, st);
       if (rc != B200FFT_OK) return rc;
     }
   }
@@ -268,7 +335,7 @@ int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in) {
     B200_CUDA_CHECK(cudaEventRecord(ev_in[slot], plan->hs[0]));
     B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[1], ev_in[slot], 0));
     if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[1], ev_out[slot], 0));  // output slot drained
-    int rc = run_passes(plan, plan->h_dev_out[slot], plan->h_dev_in[slot], nb, plan->hs[1]);
+    int rc = run_passes(plan, plan->h_dev_out[slot], plan->h_dev_in[slot], nb, plan->hs[1], b0);
     if (rc != B200FFT_OK) return rc;
     B200_CUDA_CHECK(cudaEventRecord(ev_k[slot], plan->hs[1]));
     B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[2], ev_k[slot], 0));

@@ -223,6 +223,97 @@ constexpr size_t rows_smem_bytes() {
   return sizeof(float2) * (size_t)max_exchange_elems<RL, C, RowLayoutN<N>::template type>() * (RL::count > 2 ? 2 : 1);
 }
 
+// ---- half-spectrum real transforms (last axis, even length n = 2H) -------------------------------
+// R2C: the real row x[0..n) is read as H complex z[m] = x[2m] + i x[2m+1] (the same bytes), the
+// H-point transform Z runs with its last stage landing in shared memory, and the unpack
+//     X[k] = (Z[k] + conj(Z[H-k]))/2 - (i/2) W_n^k (Z[k] - conj(Z[H-k])),  k = 0..H
+// writes the n/2+1 bins straight to global memory (one read + one write of HBM per element).
+// C2R is the mirror image: rows of n/2+1 bins are staged in shared memory, stage 0 reads
+//     Z[k] = (X[k] + conj(X[H-k])) + i W_n^{-k} (X[k] - conj(X[H-k]))
+// on the fly, and the H-point inverse writes x as interleaved pairs, scaled by 1/n.
+// `tw2` holds W_n^k (R2C) or W_n^{-k} (C2R) for k = 0..H.
+struct HalfArgs {
+  const void* in;
+  void* out;
+  const float2* tw;
+  const float2* tw2;
+  long long nrows;
+  float scale;
+};
+
+template <int H, class RL, int C, int NT>
+__global__ void __launch_bounds__(NT) rows_r2c_kernel(const __grid_constant__ HalfArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
+  constexpr int BUF = EX > C * H ? EX : C * H;
+  float2* buf0 = smem_f2;
+  float2* buf1 = smem_f2 + BUF;
+  // the last stage writes Z[o][k] densely into the buffer the last exchange did not use
+  float2* zbuf = ((RL::count - 1) % 2 == 0) ? buf0 : buf1;
+  const long long row0 = (long long)blockIdx.x * C;
+  const int valid = (int)min((long long)C, a.nrows - row0);
+  GlobalSrc<false> src{reinterpret_cast<const float2*>(a.in) + row0 * H, H, 1, valid, 1};
+  run_axis<RL, H, C, 1, NT, false, RowLayoutN<H>::template type>(src, SmemDst<PlaneLayout<H>>{zbuf}, buf0, buf1, a.tw,
+                                                                 1.f, false);
+  __syncthreads();
+  float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + row0 * (H + 1);
+  const int total = valid * (H + 1);
+  for (int idx = threadIdx.x; idx < total; idx += NT) {
+    const int o = idx / (H + 1), k = idx - o * (H + 1);
+    const float2 zk = zbuf[o * H + (k == H ? 0 : k)];
+    float2 zm = zbuf[o * H + (k == 0 ? 0 : H - k)];
+    zm.y = -zm.y;
+    const float2 s = make_float2(zk.x + zm.x, zk.y + zm.y), d = make_float2(zk.x - zm.x, zk.y - zm.y);
+    const float2 w = __ldg(&a.tw2[k]);
+    const float2 t = cmulf(d, w);  // W * (Z[k] - conj(Z[H-k]))
+    // X = (s - i t) / 2
+    out[idx] = make_float2(0.5f * (s.x + t.y), 0.5f * (s.y - t.x));
+  }
+}
+
+// stage-0 source of the C2R kernel: Z[k] from the staged half spectrum
+template <int H>
+struct HermSrc {
+  const float2* xb;  // [rows][H+1]
+  const float2* __restrict__ tw2;
+  __device__ __forceinline__ float2 load(int o, int i, int) const {
+    const float2 xk = xb[o * (H + 1) + i];
+    float2 xm = xb[o * (H + 1) + H - i];
+    xm.y = -xm.y;
+    const float2 s = make_float2(xk.x + xm.x, xk.y + xm.y), d = make_float2(xk.x - xm.x, xk.y - xm.y);
+    const float2 t = cmulf(d, __ldg(&tw2[i]));  // W_n^{-i} * (X[i] - conj(X[H-i]))
+    return make_float2(s.x - t.y, s.y + t.x);   // s + i t
+  }
+};
+
+template <int H, class RL, int C, int NT>
+__global__ void __launch_bounds__(NT) rows_c2r_kernel(const __grid_constant__ HalfArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
+  float2* buf0 = smem_f2;
+  float2* buf1 = smem_f2 + EX;
+  float2* xbuf = smem_f2 + 2 * EX;  // [C][H+1]
+  const long long row0 = (long long)blockIdx.x * C;
+  const int valid = (int)min((long long)C, a.nrows - row0);
+  const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + row0 * (H + 1);
+  for (int idx = threadIdx.x; idx < C * (H + 1); idx += NT)
+    xbuf[idx] = idx < valid * (H + 1) ? __ldg(&in[idx]) : make_float2(0.f, 0.f);
+  __syncthreads();
+  GlobalDst dst{reinterpret_cast<float2*>(a.out) + row0 * H, H, 1, valid, 1};
+  run_axis<RL, H, C, 1, NT, true, RowLayoutN<H>::template type>(HermSrc<H>{xbuf, a.tw2}, dst, buf0, buf1, a.tw, a.scale,
+                                                                true);
+}
+template <int H, class RL, int C>
+constexpr size_t rows_r2c_smem_bytes() {
+  constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
+  return sizeof(float2) * (size_t)(EX > C * H ? EX : C * H) * 2;
+}
+template <int H, class RL, int C>
+constexpr size_t rows_c2r_smem_bytes() {
+  constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
+  return sizeof(float2) * ((size_t)EX * 2 + (size_t)C * (H + 1));
+}
+
 struct ColsArgs {
   const void* in;
   float2* out;

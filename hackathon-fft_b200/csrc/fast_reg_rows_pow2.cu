@@ -5,6 +5,9 @@
 #include "fast_registry.hpp"
 namespace b200fft {
 void register_rows_pow2() {
+  reg_rows<8, 256, 256, true, 8>();
+  reg_rows<16, 128, 128, true, 16>();
+  reg_rows<32, 128, 128, true, 32>();
   reg_rows<64, 32, 256, true, 8, 8>();
   reg_rows<128, 32, 256, true, 16, 8>();
   reg_rows<128, 32, 256, true, 8, 16>();

@@ -93,8 +93,34 @@ std::vector<float2> build_twiddles(const std::vector<int>& radices, bool inverse
   return t;
 }
 
+// W_n^{+-k}, k = 0..n/2, for the R2C unpack / C2R pack
+std::vector<float2> build_half_twiddles(long long n, bool inverse) {
+  std::vector<float2> t;
+  for (long long k = 0; k <= n / 2; ++k) {
+    const double th = 2.0 * M_PI * (double)k / (double)n;
+    t.push_back(make_float2((float)std::cos(th), (float)((inverse ? 1.0 : -1.0) * std::sin(th))));
+  }
+  return t;
+}
+
+// stage list of length n with one factor 2 removed (the even/odd split the real transform uses)
+std::vector<std::vector<uint32_t>> drop_factor_two(const std::vector<uint32_t>& ordered) {
+  std::vector<std::vector<uint32_t>> out;
+  for (size_t i = 0; i < ordered.size(); ++i) {
+    if (ordered[i] % 2) continue;
+    if (i > 0 && ordered[i] == ordered[i - 1]) continue;
+    std::vector<uint32_t> o(ordered);
+    if (o[i] == 2) o.erase(o.begin() + i);
+    else o[i] /= 2;
+    out.push_back(o);
+  }
+  return out;
+}
+
 struct FastPass : Pass {
   const Variant* v = nullptr;
+  HalfMode half = HALF_NONE;
+  float2* d_tw2 = nullptr;
   AxisView view;
   bool inverse = false, real_in = false, do_scale = false;
   float scale = 1.f;
@@ -102,7 +128,19 @@ struct FastPass : Pass {
   std::string text;
 
   int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) override {
-    if (v->kind == ROWS) {
+    if (half != HALF_NONE) {
+      HalfArgs a;
+      a.in = src;
+      a.out = dst;
+      a.tw = d_tw;
+      a.tw2 = d_tw2;
+      a.nrows = nbatch * view.outer_per_batch;
+      a.scale = scale;
+      const long long grid = (a.nrows + v->tile - 1) / v->tile;
+      if (grid <= 0) return B200FFT_OK;
+      if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many row tiles");
+      v->launch_half(half == HALF_C2R, a, (unsigned)grid, stream);
+    } else if (v->kind == ROWS) {
       RowsArgs a;
       a.in = src;
       a.out = reinterpret_cast<float2*>(dst);
@@ -138,7 +176,7 @@ struct FastPass : Pass {
 }  // namespace
 
 std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
-                                     bool scale_inverse) {
+                                     bool scale_inverse, HalfMode half) {
   register_all();
   const Problem& p = plan.prob;
   if (p.desc.out_dtype != B200FFT_F32 || src.dtype != B200FFT_F32) return nullptr;
@@ -147,10 +185,20 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   const AxisSpec& ax = p.axes[axis];
 
   std::vector<const Variant*> cands;
-  for (const Variant& v : registry())
-    if (v.kind == kind && v.n == (int)view.n && (v.full || (!p.desc.inverse && src.comps == 2)) &&
-        can_group(ax.ordered, v.radices))
-      cands.push_back(&v);
+  if (half != HALF_NONE) {
+    if (kind != ROWS || view.n % 2) return nullptr;
+    const auto reduced = drop_factor_two(ax.ordered);
+    for (const Variant& v : registry()) {
+      if (v.kind != ROWS || v.n != (int)(view.n / 2) || !v.launch_half) continue;
+      for (const auto& o : reduced)
+        if (can_group(o, v.radices)) { cands.push_back(&v); break; }
+    }
+  } else {
+    for (const Variant& v : registry())
+      if (v.kind == kind && v.n == (int)view.n && (v.full || (!p.desc.inverse && src.comps == 2)) &&
+          can_group(ax.ordered, v.radices))
+        cands.push_back(&v);
+  }
   if (cands.empty()) return nullptr;
   if (const char* pref = getenv("B200FFT_PREFER")) {
     std::string s(pref);
@@ -172,7 +220,7 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
     });
   }
   const Variant* v = cands[0];
-  if (v->prepare(v->smem) != cudaSuccess) {
+  if ((half != HALF_NONE ? v->prepare_half() : v->prepare(v->smem)) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
@@ -183,16 +231,29 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   pass->real_in = src.comps == 1;
   pass->do_scale = scale_inverse;
   pass->scale = scale_inverse ? (float)(1.0 / (double)view.n) : 1.f;
-  std::vector<float2> tw = build_twiddles(v->radices, pass->inverse);
+  pass->half = half;
+  if (half != HALF_NONE) {
+    if (half == HALF_C2R) pass->scale = (float)(1.0 / (double)view.n);  // 1/(2H): the inverse is always normalised
+    std::vector<float2> tw2 = build_half_twiddles(view.n, half == HALF_C2R);
+    if (cudaMalloc(&pass->d_tw2, tw2.size() * sizeof(float2)) != cudaSuccess) return nullptr;
+    plan.owned_device.push_back(pass->d_tw2);
+    if (cudaMemcpy(pass->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  }
+  std::vector<float2> tw = build_twiddles(v->radices, half == HALF_NONE ? pass->inverse : half == HALF_C2R);
   if (cudaMalloc(&pass->d_tw, tw.size() * sizeof(float2)) != cudaSuccess) return nullptr;
   if (cudaMemcpy(pass->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
   plan.owned_device.push_back(pass->d_tw);
   std::string stages;
   for (uint32_t r : ax.ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
   char buf[320];
-  snprintf(buf, sizeof buf, "axis %d: %s n=%lld inner=%lld smem=%zuB user stages=[%s] fused as (%s)%s", axis,
-           v->name.c_str(), (long long)view.n, (long long)view.inner, v->smem, stages.c_str(),
-           radix_name(v->radices).c_str(), pass->real_in ? " real-in" : "");
+  if (half != HALF_NONE)
+    snprintf(buf, sizeof buf, "axis %d: %s[%s] n=%lld (as %d complex) smem=%zuB user stages=[%s] fused as (2)(%s)", axis,
+             half == HALF_R2C ? "r2c" : "c2r", v->name.c_str(), (long long)view.n, v->n,
+             half == HALF_R2C ? v->smem_r2c : v->smem_c2r, stages.c_str(), radix_name(v->radices).c_str());
+  else
+    snprintf(buf, sizeof buf, "axis %d: %s n=%lld inner=%lld smem=%zuB user stages=[%s] fused as (%s)%s", axis,
+             v->name.c_str(), (long long)view.n, (long long)view.inner, v->smem, stages.c_str(),
+             radix_name(v->radices).c_str(), pass->real_in ? " real-in" : "");
   pass->text = buf;
   return pass;
 }

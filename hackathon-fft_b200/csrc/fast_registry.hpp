@@ -23,6 +23,10 @@ struct Variant {
   void (*launch_cols)(bool, bool, const ColsArgs&, unsigned, size_t, cudaStream_t);
   cudaError_t (*prepare)(size_t);
   bool full;  // has inverse and real-input instantiations
+  // half-spectrum real transforms of length 2*n on top of this n-point row variant (FULL only)
+  void (*launch_half)(bool c2r, const HalfArgs&, unsigned, cudaStream_t) = nullptr;
+  cudaError_t (*prepare_half)() = nullptr;
+  size_t smem_r2c = 0, smem_c2r = 0;
 };
 
 std::vector<Variant>& registry();
@@ -49,6 +53,20 @@ struct RowsV {
       if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, false>, attr, (int)smem);
       if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, true>, attr, (int)smem);
     }
+    return e;
+  }
+};
+
+template <int H, class RL, int C, int NT>
+struct HalfV {
+  static void launch(bool c2r, const HalfArgs& a, unsigned grid, cudaStream_t st) {
+    if (c2r) rows_c2r_kernel<H, RL, C, NT><<<grid, NT, rows_c2r_smem_bytes<H, RL, C>(), st>>>(a);
+    else rows_r2c_kernel<H, RL, C, NT><<<grid, NT, rows_r2c_smem_bytes<H, RL, C>(), st>>>(a);
+  }
+  static cudaError_t prepare() {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(rows_r2c_kernel<H, RL, C, NT>, attr, (int)rows_r2c_smem_bytes<H, RL, C>());
+    if (!e) e = cudaFuncSetAttribute(rows_c2r_kernel<H, RL, C, NT>, attr, (int)rows_c2r_smem_bytes<H, RL, C>());
     return e;
   }
 };
@@ -97,6 +115,14 @@ void reg_rows() {
   v.launch_rows = &RowsV<N, RL, C, NT, FULL>::launch;
   v.launch_cols = nullptr;
   v.prepare = &RowsV<N, RL, C, NT, FULL>::prepare;
+  if constexpr (FULL) {
+    v.smem_r2c = rows_r2c_smem_bytes<N, RL, C>();
+    v.smem_c2r = rows_c2r_smem_bytes<N, RL, C>();
+    if (v.smem_r2c <= 227 * 1024 && v.smem_c2r <= 227 * 1024) {
+      v.launch_half = &HalfV<N, RL, C, NT>::launch;
+      v.prepare_half = &HalfV<N, RL, C, NT>::prepare;
+    }
+  }
   v.full = FULL;
   registry().push_back(v);
 }

@@ -32,6 +32,8 @@ struct GenParams {
   const void* tw;
   long long outer, inner, tiles_per_outer, ntiles;
   int n, nstages, C, row, src_dtype, src_comps;
+  int half;  // HalfMode (rows only): R2C stores bins 0..n/2 with row pitch n/2+1; C2R loads the
+             // half spectrum with Hermitian extension X[n-k] = conj(X[k]) and stores real parts
   double scale;
   int radix[GEN_MAX_STAGES];
 };
@@ -50,12 +52,24 @@ __global__ void __launch_bounds__(GEN_THREADS) gen_fft_kernel(const __grid_const
   for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     long long base, sn, sc;
     int cc;
+    const int hb = n / 2 + 1;  // bins of a half spectrum
     if (p.row) {
       const long long o0 = tile * p.C;
       cc = (int)min((long long)p.C, p.outer - o0);
       base = o0 * n;
       sn = 1;
       sc = n;
+      if (p.half == HALF_C2R) {
+        // Hermitian-extended load of rows that hold n/2+1 bins
+        for (int f = tid; f < n * cc; f += GEN_THREADS) {
+          const int c = f / n, nn = f - c * n;
+          const long long rowb = (o0 + c) * hb;
+          T2 v;
+          if (nn < hb) v = load_any<T>(p.src, p.src_dtype, 2, rowb + nn);
+          else { v = load_any<T>(p.src, p.src_dtype, 2, rowb + (n - nn)); v.y = -v.y; }
+          buf0[f] = v;
+        }
+      }
     } else {
       const long long o = tile / p.tiles_per_outer;
       const long long i0 = (tile - o * p.tiles_per_outer) * p.C;
@@ -68,11 +82,13 @@ __global__ void __launch_bounds__(GEN_THREADS) gen_fft_kernel(const __grid_const
 
     // stage the tile: shared index == flat index f in both layouts
     // (rows: [c][n], n fastest; strided: [n][cc], c fastest)
-    for (int f = tid; f < total; f += GEN_THREADS) {
-      int nn, c;
-      if (p.row) { c = f / n; nn = f - c * n; }
-      else { nn = f / cc; c = f - nn * cc; }
-      buf0[f] = load_any<T>(p.src, p.src_dtype, p.src_comps, base + nn * sn + c * sc);
+    if (!(p.row && p.half == HALF_C2R)) {
+      for (int f = tid; f < total; f += GEN_THREADS) {
+        int nn, c;
+        if (p.row) { c = f / n; nn = f - c * n; }
+        else { nn = f / cc; c = f - nn * cc; }
+        buf0[f] = load_any<T>(p.src, p.src_dtype, p.src_comps, base + nn * sn + c * sc);
+      }
     }
     __syncthreads();
 
@@ -107,11 +123,21 @@ __global__ void __launch_bounds__(GEN_THREADS) gen_fft_kernel(const __grid_const
       P = Q;
     }
 
-    for (int f = tid; f < total; f += GEN_THREADS) {
-      int nn, c;
-      if (p.row) { c = f / n; nn = f - c * n; }
-      else { nn = f / cc; c = f - nn * cc; }
-      dst[base + nn * sn + c * sc] = cur[f];
+    if (p.row && p.half == HALF_R2C) {
+      for (int f = tid; f < hb * cc; f += GEN_THREADS) {
+        const int c = f / hb, nn = f - c * hb;
+        dst[(tile * p.C + c) * hb + nn] = cur[c * n + nn];
+      }
+    } else if (p.row && p.half == HALF_C2R) {
+      T* __restrict__ rdst = reinterpret_cast<T*>(p.dst);
+      for (int f = tid; f < total; f += GEN_THREADS) rdst[base + f] = cur[f].x;
+    } else {
+      for (int f = tid; f < total; f += GEN_THREADS) {
+        int nn, c;
+        if (p.row) { c = f / n; nn = f - c * n; }
+        else { nn = f / cc; c = f - nn * cc; }
+        dst[base + nn * sn + c * sc] = cur[f];
+      }
     }
     __syncthreads();
   }
@@ -155,7 +181,7 @@ struct GenericPass : Pass {
 }  // namespace
 
 std::unique_ptr<Pass> make_generic_pass(const b200fft_plan& plan, int axis, const AxisView& view,
-                                        const IoSpec& src, bool scale_inverse) {
+                                        const IoSpec& src, bool scale_inverse, HalfMode half) {
   const AxisSpec& ax = plan.prob.axes[axis];
   const bool f64 = plan.prob.desc.out_dtype == B200FFT_F64;
   const size_t sz = f64 ? 16 : 8;
@@ -180,6 +206,7 @@ std::unique_ptr<Pass> make_generic_pass(const b200fft_plan& plan, int axis, cons
   for (int s = 0; s < p.nstages; ++s) p.radix[s] = (int)ax.ordered[s];
   p.src_dtype = src.dtype;
   p.src_comps = src.comps;
+  p.half = (int)half;
   p.scale = scale_inverse ? 1.0 / (double)view.n : 1.0;
   int C;
   if (p.row) {
@@ -209,8 +236,9 @@ std::unique_ptr<Pass> make_generic_pass(const b200fft_plan& plan, int axis, cons
   char buf[256];
   std::string radices;
   for (uint32_t r : ax.ordered) radices += (radices.empty() ? "" : ",") + std::to_string(r);
-  snprintf(buf, sizeof buf, "axis %d: generic<%s> n=%lld inner=%lld tile=%d smem=%zuB stages=[%s]", axis,
-           f64 ? "f64" : "f32", (long long)view.n, (long long)view.inner, C, pass->smem, radices.c_str());
+  snprintf(buf, sizeof buf, "axis %d: generic<%s>%s n=%lld inner=%lld tile=%d smem=%zuB stages=[%s]", axis,
+           f64 ? "f64" : "f32", half == HALF_R2C ? " r2c" : half == HALF_C2R ? " c2r" : "", (long long)view.n,
+           (long long)view.inner, C, pass->smem, radices.c_str());
   pass->text = buf;
   return pass;
 }

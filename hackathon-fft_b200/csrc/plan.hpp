@@ -33,13 +33,19 @@ struct Scatter {
   int my_rank = 0;
 };
 
+// which buffer a pass reads / writes
+enum BufSel { BUF_INPUT = 0, BUF_OUTPUT = 1, BUF_WORK = 2 };
+
+// Half-spectrum handling of the last axis (B200FFT_REAL_HALF)
+enum HalfMode { HALF_NONE = 0, HALF_R2C = 1, HALF_C2R = 2 };
+
 struct Pass {
   virtual ~Pass() {}
   // Run this pass for `nbatch` batch items. src/dst already point at the first item.
   virtual int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) = 0;
   virtual std::string describe() const = 0;
   virtual int launches() const { return 1; }
-  bool reads_input = false;  // src is the user's input buffer (else: dst, in place)
+  BufSel src_sel = BUF_OUTPUT, dst_sel = BUF_OUTPUT;
 };
 
 struct DeviceTwiddles {
@@ -58,6 +64,7 @@ struct b200fft_plan {
   std::vector<void*> owned_device;          // misc device allocations freed at destroy
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
+  size_t work_stride = 0;     // workspace bytes per batch item
   int64_t chunk_batches = 0;  // >0: run all passes per chunk of this many batch items (L2 residency)
   // exec_host resources (lazily created)
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
@@ -71,10 +78,11 @@ struct b200fft_plan {
 namespace b200fft {
 
 // kernel families (each returns nullptr when it does not cover the request)
+// `half`: HALF_R2C = rows of n reals -> n/2+1 complex bins; HALF_C2R = the inverse (rows only).
 std::unique_ptr<Pass> make_generic_pass(const b200fft_plan& plan, int axis, const AxisView& view,
-                                        const IoSpec& src, bool scale_inverse);
+                                        const IoSpec& src, bool scale_inverse, HalfMode half = HALF_NONE);
 // compile-time kernels (fast_registry.cu); allocates its stage twiddle table into plan.owned_device
 std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
-                                     bool scale_inverse);
+                                     bool scale_inverse, HalfMode half = HALF_NONE);
 
 }  // namespace b200fft
