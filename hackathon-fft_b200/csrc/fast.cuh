@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "dft.cuh"
+#include "tma.cuh"
 
 namespace b200fft {
 
@@ -221,6 +222,67 @@ __global__ void __launch_bounds__(NT) rows_kernel(const __grid_constant__ RowsAr
 template <int N, class RL, int C>
 constexpr size_t rows_smem_bytes() {
   return sizeof(float2) * (size_t)max_exchange_elems<RL, C, RowLayoutN<N>::template type>() * (RL::count > 2 ? 2 : 1);
+}
+
+// strided axis, TMA-tiled: the tile [N][CW] is fetched by cp.async.bulk.tensor.3d box loads (tensor
+// map over the (inner, N, outer) view of the array) into shared memory, completion on an mbarrier;
+// every stage runs shared -> registers -> shared, and the finished tile leaves through a TMA store.
+// No thread issues a global load or store: the strided-axis "transpose" is done by the TMA unit.
+struct ColsTmaArgs {
+  const float2* tw;
+  int tiles_per_outer;
+  float scale;
+  int do_scale;
+};
+
+constexpr int tma_box_rows(int n) {
+  int r = n < 256 ? n : 256;
+  while (n % r) --r;
+  return r;
+}
+
+template <int N, class RL, int CW, int NT, bool INV>
+__global__ void __launch_bounds__(NT) cols_tma_kernel(const __grid_constant__ CUtensorMap map_in,
+                                                      const __grid_constant__ CUtensorMap map_out,
+                                                      const __grid_constant__ ColsTmaArgs a) {
+  extern __shared__ __align__(128) float2 smem_f2[];
+  __shared__ __align__(8) uint64_t bar;
+  constexpr int BR = tma_box_rows(N);
+  constexpr int TILE = N * CW;
+  float2* b0 = smem_f2;
+  float2* b1 = smem_f2 + TILE;
+  const int o = blockIdx.x / a.tiles_per_outer;
+  const int c0 = (blockIdx.x - o * a.tiles_per_outer) * CW;
+  if (threadIdx.x == 0) {
+    tma::prefetch_map(&map_in);
+    tma::prefetch_map(&map_out);
+    tma::mbar_init(&bar, 1);
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma::mbar_arrive_expect_tx(&bar, TILE * (uint32_t)sizeof(float2));
+#pragma unroll
+    for (int b = 0; b < N / BR; ++b) tma::load_3d(b0 + b * BR * CW, &map_in, c0, b * BR, o, &bar);
+  }
+  tma::mbar_wait(&bar, 0);
+  // stage s reads buffer s % 2 and writes buffer (s + 1) % 2; the result ends in buffer S % 2
+  float2* res = (RL::count % 2 == 0) ? b0 : b1;
+  using L = DenseLayout<N, CW>;
+  run_axis<RL, N, 1, CW, NT, INV, DenseLayoutN<N, CW>::template type, /*E0=*/1>(SmemSrc<L>{b0}, SmemDst<L>{res}, b0, b1,
+                                                                                 a.tw, a.scale, a.do_scale != 0);
+  tma::fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int b = 0; b < N / BR; ++b) tma::store_3d(&map_out, res + b * BR * CW, c0, b * BR, o);
+    tma::store_commit();
+    tma::store_wait_read();
+  }
+}
+template <int N, int CW>
+constexpr size_t cols_tma_smem_bytes() {
+  return sizeof(float2) * (size_t)N * CW * 2;
 }
 
 // ---- half-spectrum real transforms (last axis, even length n = 2H) -------------------------------

@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <cudaTypedefs.h>
+
 #include "fast_registry.hpp"
 #include "plan.hpp"
 
@@ -29,6 +31,7 @@ void register_rows_pow2();
 void register_rows_mixed();
 void register_cols_pow2();
 void register_cols_mixed();
+void register_cols_tma();
 
 namespace {
 
@@ -40,6 +43,7 @@ void register_all() {
   register_rows_mixed();
   register_cols_pow2();
   register_cols_mixed();
+  register_cols_tma();
 }
 
 // can `target` (super-stage radices) be formed by partitioning `ordered` (the user's stage
@@ -117,6 +121,33 @@ std::vector<std::vector<uint32_t>> drop_factor_two(const std::vector<uint32_t>& 
   return out;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }();
+  return fn;
+}
+
+// tensor map over the (inner, N, outer) view of a dense complex64 array; box = (CW, box_rows, 1)
+bool encode_axis_map(CUtensorMap* map, const void* base, long long inner, long long n, long long outer, int cw,
+                     int box_rows) {
+  auto enc = tensor_map_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)n, (cuuint64_t)outer};
+  cuuint64_t strides[2] = {(cuuint64_t)inner * 8, (cuuint64_t)inner * (cuuint64_t)n * 8};
+  cuuint32_t box[3] = {(cuuint32_t)cw, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct FastPass : Pass {
   const Variant* v = nullptr;
   HalfMode half = HALF_NONE;
@@ -152,6 +183,21 @@ struct FastPass : Pass {
       if (grid <= 0) return B200FFT_OK;
       if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many row tiles");
       v->launch_rows(inverse, real_in, a, (unsigned)grid, v->smem, stream);
+    } else if (v->kind == COLS_TMA) {
+      const long long outer = nbatch * view.outer_per_batch;
+      CUtensorMap mi, mo;
+      if (!encode_axis_map(&mi, src, view.inner, view.n, outer, v->tile, v->box_rows) ||
+          !encode_axis_map(&mo, dst, view.inner, view.n, outer, v->tile, v->box_rows))
+        return fail(B200FFT_ERR_CUDA, "cuTensorMapEncodeTiled failed for the strided-axis pass");
+      ColsTmaArgs a;
+      a.tw = d_tw;
+      a.tiles_per_outer = (int)((view.inner + v->tile - 1) / v->tile);
+      a.scale = scale;
+      a.do_scale = do_scale;
+      const long long grid = outer * a.tiles_per_outer;
+      if (grid <= 0) return B200FFT_OK;
+      if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many column tiles");
+      v->launch_cols_tma(inverse, mi, mo, a, (unsigned)grid, v->smem, stream);
     } else {
       ColsArgs a;
       a.in = src;
@@ -194,10 +240,15 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
         if (can_group(o, v.radices)) { cands.push_back(&v); break; }
     }
   } else {
-    for (const Variant& v : registry())
-      if (v.kind == kind && v.n == (int)view.n && (v.full || (!p.desc.inverse && src.comps == 2)) &&
+    // TMA tiles need 16-byte global strides (even inner), complex fp32 source, a usable encoder
+    const bool tma_ok = kind == COLS && src.comps == 2 && view.inner % 2 == 0 && tensor_map_encoder() != nullptr &&
+                        (unsigned long long)view.inner * view.n * 8 < (1ull << 40);
+    for (const Variant& v : registry()) {
+      const bool kind_ok = v.kind == kind || (v.kind == COLS_TMA && tma_ok);
+      if (kind_ok && v.n == (int)view.n && (v.full || (!p.desc.inverse && src.comps == 2)) &&
           can_group(ax.ordered, v.radices))
         cands.push_back(&v);
+    }
   }
   if (cands.empty()) return nullptr;
   if (const char* pref = getenv("B200FFT_PREFER")) {

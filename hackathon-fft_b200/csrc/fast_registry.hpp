@@ -9,7 +9,7 @@
 
 namespace b200fft {
 
-enum Kind { ROWS = 0, COLS = 1 };
+enum Kind { ROWS = 0, COLS = 1, COLS_TMA = 2 };
 
 struct Variant {
   std::string name;
@@ -22,6 +22,9 @@ struct Variant {
   void (*launch_rows)(bool, bool, const RowsArgs&, unsigned, size_t, cudaStream_t);
   void (*launch_cols)(bool, bool, const ColsArgs&, unsigned, size_t, cudaStream_t);
   cudaError_t (*prepare)(size_t);
+  void (*launch_cols_tma)(bool, const CUtensorMap&, const CUtensorMap&, const ColsTmaArgs&, unsigned, size_t,
+                          cudaStream_t) = nullptr;
+  int box_rows = 0;  // TMA box extent along the transform axis
   bool full;  // has inverse and real-input instantiations
   // half-spectrum real transforms of length 2*n on top of this n-point row variant (FULL only)
   void (*launch_half)(bool c2r, const HalfArgs&, unsigned, cudaStream_t) = nullptr;
@@ -94,6 +97,21 @@ struct ColsV {
   }
 };
 
+template <int N, class RL, int CW, int NT>
+struct ColsTmaV {
+  static void launch(bool inv, const CUtensorMap& mi, const CUtensorMap& mo, const ColsTmaArgs& a, unsigned grid,
+                     size_t smem, cudaStream_t st) {
+    if (inv) cols_tma_kernel<N, RL, CW, NT, true><<<grid, NT, smem, st>>>(mi, mo, a);
+    else cols_tma_kernel<N, RL, CW, NT, false><<<grid, NT, smem, st>>>(mi, mo, a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(cols_tma_kernel<N, RL, CW, NT, false>, attr, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(cols_tma_kernel<N, RL, CW, NT, true>, attr, (int)smem);
+    return e;
+  }
+};
+
 template <class RL>
 std::vector<int> radix_vec() {
   return std::vector<int>(RL::r, RL::r + RL::count);
@@ -141,5 +159,22 @@ void reg_cols() {
   registry().push_back(v);
 }
 
+
+template <int N, int CW, int NT, int... Rs>
+void reg_cols_tma() {
+  using RL = Radices<Rs...>;
+  static_assert(RL::product() == N, "radices must multiply to N");
+  Variant v;
+  v.kind = COLS_TMA; v.n = N; v.radices = radix_vec<RL>(); v.tile = CW; v.threads = NT;
+  v.smem = cols_tma_smem_bytes<N, CW>();
+  v.name = "colsT" + std::to_string(N) + "_" + radix_name(v.radices) + "_w" + std::to_string(CW) + "_t" + std::to_string(NT);
+  v.launch_rows = nullptr;
+  v.launch_cols = nullptr;
+  v.launch_cols_tma = &ColsTmaV<N, RL, CW, NT>::launch;
+  v.prepare = &ColsTmaV<N, RL, CW, NT>::prepare;
+  v.box_rows = tma_box_rows(N);
+  v.full = true;
+  registry().push_back(v);
+}
 
 }  // namespace b200fft
