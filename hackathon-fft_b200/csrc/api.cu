@@ -103,6 +103,7 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
     if (!pass) return B200FFT_ERR_UNSUPPORTED;
     pass->src_sel = ssel;
     pass->dst_sel = dsel;
+    pass->axis = axis;
     plan->passes.push_back(std::move(pass));
     return B200FFT_OK;
   };
@@ -293,8 +294,54 @@ int b200fft_exec(b200fft_plan* plan, void* d_out, const void* d_in, void* cu_str
   return run_passes(plan, d_out, d_in, plan->prob.batch, (cudaStream_t)cu_stream);
 }
 
-int b200fft_exec_scatter(b200fft_plan*, void* const*, int, int, const void*, void*) {
-  return fail(B200FFT_ERR_UNSUPPORTED, "exec_scatter is not built yet");
+int b200fft_exec_scatter(b200fft_plan* plan, void* const* peer_out, int npeers, int my_rank, const void* d_in,
+                         void* d_work, void* cu_stream) {
+  if (!plan || !peer_out || !d_in || !d_work) return fail(B200FFT_ERR_INVALID_ARG, "null plan or buffer");
+  if (plan->prob.half) return fail(B200FFT_ERR_UNSUPPORTED, "exec_scatter takes a complex plan");
+  if (my_rank < 0 || my_rank >= npeers) return fail(B200FFT_ERR_INVALID_ARG, "my_rank %d outside 0..%d", my_rank, npeers);
+  if (plan->passes.empty() || plan->passes.back()->axis != 0)
+    return fail(B200FFT_ERR_INVALID_ARG, "exec_scatter: the plan's last pass must transform axis 0 (the split axis)");
+  DeviceGuard guard(plan->device);
+  cudaStream_t st = (cudaStream_t)cu_stream;
+  const size_t n = plan->passes.size();
+  for (size_t i = 0; i + 1 < n; ++i) {
+    Pass& pass = *plan->passes[i];
+    int rc = pass.launch(pass.src_sel == BUF_INPUT ? d_in : (const void*)d_work, d_work, plan->prob.batch, st);
+    if (rc != B200FFT_OK) return rc;
+  }
+  Pass& last = *plan->passes.back();
+  Scatter sc;
+  sc.peer_out = peer_out;
+  sc.npeers = npeers;
+  sc.my_rank = my_rank;
+  return last.launch_scatter(last.src_sel == BUF_INPUT ? d_in : (const void*)d_work, sc, plan->prob.batch, st);
+}
+
+int b200fft_malloc(void** d_ptr, size_t bytes) {
+  if (!d_ptr) return fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+  B200_CUDA_CHECK(cudaMalloc(d_ptr, bytes));
+  return B200FFT_OK;
+}
+int b200fft_free(void* d_ptr) {
+  B200_CUDA_CHECK(cudaFree(d_ptr));
+  return B200FFT_OK;
+}
+int b200fft_ipc_export(void* d_ptr, unsigned char handle[B200FFT_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == B200FFT_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  B200_CUDA_CHECK(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle, &h, sizeof h);
+  return B200FFT_OK;
+}
+int b200fft_ipc_open(const unsigned char handle[B200FFT_IPC_HANDLE_BYTES], void** d_ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  B200_CUDA_CHECK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200FFT_OK;
+}
+int b200fft_ipc_close(void* d_ptr) {
+  B200_CUDA_CHECK(cudaIpcCloseMemHandle(d_ptr));
+  return B200FFT_OK;
 }
 
 // Host-buffer execution: the batch is cut into chunks that flow through

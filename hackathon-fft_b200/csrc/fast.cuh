@@ -405,6 +405,47 @@ __global__ void __launch_bounds__(NT) cols_kernel(const __grid_constant__ ColsAr
   run_axis<RL, N, 1, CW, NT, INV, DenseLayoutN<N, CW>::template type>(src, dst, buf0, buf1, a.tw, a.scale,
                                                                       a.do_scale != 0);
 }
+// strided axis with a scattering store: the slab decomposition's exchange fused into the pass.
+// The tile's output row i (index along the transformed axis, which is the axis being split across
+// GPUs) belongs to peer h = i / yl; it is written straight into that peer's buffer at the place it
+// has in the peer's [z][yl][x] slab. With peer pointers mapped over NVLink (CUDA IPC) the
+// all-to-all happens inside this kernel's stores; with all pointers local it is the pack step of
+// an NCCL all-to-all.
+struct ScatterArgs {
+  float2* peer[16];
+  int yl;            // rows of the split axis per peer
+  long long zbase;   // first outer index (z plane) of this rank in the peers' slabs
+};
+struct ScatterDst {
+  const ScatterArgs* sa;
+  long long tile_off;  // ((zbase + o) * yl) * inner + c0
+  long long inner;
+  int valid_c;
+  __device__ __forceinline__ void store(int, int i, int c, float2 v) const {
+    if (c >= valid_c) return;
+    const int h = i / sa->yl;
+    const int r = i - h * sa->yl;
+    sa->peer[h][tile_off + r * inner + c] = v;
+  }
+};
+
+template <int N, class RL, int CW, int NT, bool INV>
+__global__ void __launch_bounds__(NT) cols_scatter_kernel(const __grid_constant__ ColsArgs a,
+                                                          const __grid_constant__ ScatterArgs sa) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
+  float2* buf0 = smem_f2;
+  float2* buf1 = smem_f2 + BUF;
+  const long long o = blockIdx.x / a.tiles_per_outer;
+  const long long c0 = (long long)(blockIdx.x - o * a.tiles_per_outer) * CW;
+  const long long base = o * N * a.inner + c0;
+  const int valid_c = (int)min((long long)CW, a.inner - c0);
+  GlobalSrc<false> src{reinterpret_cast<const float2*>(a.in) + base, 0, a.inner, 1, valid_c};
+  ScatterDst dst{&sa, ((sa.zbase + o) * sa.yl) * a.inner + c0, a.inner, valid_c};
+  run_axis<RL, N, 1, CW, NT, INV, DenseLayoutN<N, CW>::template type>(src, dst, buf0, buf1, a.tw, a.scale,
+                                                                      a.do_scale != 0);
+}
+
 template <int N, class RL, int CW>
 constexpr size_t cols_smem_bytes() {
   return sizeof(float2) * (size_t)max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>() *

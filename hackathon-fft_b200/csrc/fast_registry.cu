@@ -216,6 +216,32 @@ struct FastPass : Pass {
     B200_CUDA_CHECK(cudaGetLastError());
     return B200FFT_OK;
   }
+  int launch_scatter(const void* src, const Scatter& sc, int64_t nbatch, cudaStream_t stream) override {
+    if (v->kind != COLS || !v->launch_scatter || half != HALF_NONE || real_in)
+      return fail(B200FFT_ERR_UNSUPPORTED, "no scattering store for %s", text.c_str());
+    if (sc.npeers < 1 || sc.npeers > 16 || view.n % sc.npeers)
+      return fail(B200FFT_ERR_INVALID_ARG, "split axis length %lld is not divisible by %d peers", (long long)view.n, sc.npeers);
+    ColsArgs a;
+    a.in = src;
+    a.out = nullptr;
+    a.tw = d_tw;
+    a.inner = view.inner;
+    a.tiles_per_outer = (int)((view.inner + v->tile - 1) / v->tile);
+    a.scale = scale;
+    a.do_scale = do_scale;
+    ScatterArgs sa;
+    for (int i = 0; i < 16; ++i) sa.peer[i] = i < sc.npeers ? reinterpret_cast<float2*>(sc.peer_out[i]) : nullptr;
+    sa.yl = (int)(view.n / sc.npeers);
+    const long long outer = nbatch * view.outer_per_batch;
+    sa.zbase = (long long)sc.my_rank * outer;
+    const long long grid = outer * a.tiles_per_outer;
+    if (grid <= 0) return B200FFT_OK;
+    if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many column tiles");
+    v->launch_scatter(inverse, a, sa, (unsigned)grid, v->smem, stream);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    B200_CUDA_CHECK(cudaGetLastError());
+    return B200FFT_OK;
+  }
   std::string describe() const override { return text; }
 };
 

@@ -25,6 +25,7 @@ struct Variant {
   void (*launch_cols_tma)(bool, const CUtensorMap&, const CUtensorMap&, const ColsTmaArgs&, unsigned, size_t,
                           cudaStream_t) = nullptr;
   int box_rows = 0;  // TMA box extent along the transform axis
+  void (*launch_scatter)(bool, const ColsArgs&, const ScatterArgs&, unsigned, size_t, cudaStream_t) = nullptr;
   bool full;  // has inverse and real-input instantiations
   // half-spectrum real transforms of length 2*n on top of this n-point row variant (FULL only)
   void (*launch_half)(bool c2r, const HalfArgs&, unsigned, cudaStream_t) = nullptr;
@@ -98,6 +99,20 @@ struct ColsV {
 };
 
 template <int N, class RL, int CW, int NT>
+struct ColsScatterV {
+  static void launch(bool inv, const ColsArgs& a, const ScatterArgs& sa, unsigned grid, size_t smem, cudaStream_t st) {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (inv) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(cols_scatter_kernel<N, RL, CW, NT, true>, attr, (int)smem);
+      cols_scatter_kernel<N, RL, CW, NT, true><<<grid, NT, smem, st>>>(a, sa);
+    } else {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(cols_scatter_kernel<N, RL, CW, NT, false>, attr, (int)smem);
+      cols_scatter_kernel<N, RL, CW, NT, false><<<grid, NT, smem, st>>>(a, sa);
+    }
+  }
+};
+
+template <int N, class RL, int CW, int NT>
 struct ColsTmaV {
   static void launch(bool inv, const CUtensorMap& mi, const CUtensorMap& mo, const ColsTmaArgs& a, unsigned grid,
                      size_t smem, cudaStream_t st) {
@@ -155,6 +170,7 @@ void reg_cols() {
   v.launch_rows = nullptr;
   v.launch_cols = &ColsV<N, RL, CW, NT, FULL>::launch;
   v.prepare = &ColsV<N, RL, CW, NT, FULL>::prepare;
+  if constexpr (FULL) v.launch_scatter = &ColsScatterV<N, RL, CW, NT>::launch;
   v.full = FULL;
   registry().push_back(v);
 }

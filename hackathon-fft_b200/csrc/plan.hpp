@@ -45,6 +45,12 @@ struct Pass {
   virtual int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) = 0;
   virtual std::string describe() const = 0;
   virtual int launches() const { return 1; }
+  // Same pass, but output row i of the transformed axis goes to sc.peer_out[i / rows_per_peer]
+  // (slab exchange fused into the store). Only strided fast passes implement it.
+  virtual int launch_scatter(const void*, const Scatter&, int64_t, cudaStream_t) {
+    return fail(B200FFT_ERR_UNSUPPORTED, "this pass has no scattering store (%s)", describe().c_str());
+  }
+  int axis = -1;
   BufSel src_sel = BUF_OUTPUT, dst_sel = BUF_OUTPUT;
 };
 

@@ -60,7 +60,12 @@ SYMBOLS = [
     ("b200fft_plan_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_Desc)]),
     ("b200fft_exec", ctypes.c_int, [_vp, _vp, _vp, _vp]),
     ("b200fft_exec_host", ctypes.c_int, [_vp, _vp, _vp]),
-    ("b200fft_exec_scatter", ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    ("b200fft_exec_scatter", ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    ("b200fft_malloc", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_size_t]),
+    ("b200fft_free", ctypes.c_int, [_vp]),
+    ("b200fft_ipc_export", ctypes.c_int, [_vp, ctypes.c_char_p]),
+    ("b200fft_ipc_open", ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    ("b200fft_ipc_close", ctypes.c_int, [_vp]),
     ("b200fft_plan_destroy", ctypes.c_int, [_vp]),
     ("b200fft_plan_workspace_bytes", ctypes.c_size_t, [_vp]),
     ("b200fft_plan_get_bases", ctypes.c_int, [_vp, ctypes.c_int, _u32p, ctypes.c_int]),
@@ -111,6 +116,33 @@ def _dtype_code(dt):
         return {"uint8": U8, "float32": F32, "float64": F64}[name]
     except KeyError:
         raise B200FFTError(1, "unsupported dtype %r (uint8, float32, float64)" % (dt,))
+
+
+def device_malloc(nbytes):
+    """cudaMalloc through the library: a buffer whose base can be exported over CUDA IPC."""
+    p = ctypes.c_void_p()
+    _check(lib().b200fft_malloc(ctypes.byref(p), nbytes))
+    return p.value
+
+
+def device_free(ptr):
+    _check(lib().b200fft_free(ptr))
+
+
+def ipc_export(ptr):
+    buf = ctypes.create_string_buffer(64)
+    _check(lib().b200fft_ipc_export(ptr, buf))
+    return buf.raw
+
+
+def ipc_open(handle):
+    p = ctypes.c_void_p()
+    _check(lib().b200fft_ipc_open(handle, ctypes.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr):
+    _check(lib().b200fft_ipc_close(ptr))
 
 
 def ordered_bases(length, bases):
@@ -222,9 +254,10 @@ class Plan:
     def exec_host(self, h_out, h_in):
         _check(lib().b200fft_exec_host(self._h, _ptr(h_out), _ptr(h_in)))
 
-    def exec_scatter(self, peer_ptrs, my_rank, x, stream=None):
+    def exec_scatter(self, peer_ptrs, my_rank, x, work, stream=None):
+        """Local slab transform with the exchange fused into the last pass's store (see b200fft.h)."""
         arr = (ctypes.c_void_p * len(peer_ptrs))(*[_ptr(p) for p in peer_ptrs])
-        _check(lib().b200fft_exec_scatter(self._h, arr, len(peer_ptrs), my_rank, _ptr(x), _ptr(stream)))
+        _check(lib().b200fft_exec_scatter(self._h, arr, len(peer_ptrs), my_rank, _ptr(x), _ptr(work), _ptr(stream)))
 
     def bases(self, axis):
         out = (ctypes.c_uint32 * 64)()

@@ -113,12 +113,26 @@ B200FFT_API int b200fft_exec(b200fft_plan* plan, void* d_out, const void* d_in, 
  * end-to-end call bench.py times as `e2e`. */
 B200FFT_API int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in);
 
-/* Slab-decomposition helper (multi-GPU, one process per GPU): run the plan but store
- * the result of the LAST pass directly into peer-mapped buffers. Output element with
- * index y along axis `split_axis` goes to peer_out[y / (dims[split_axis]/npeers)], at the
- * position it has in that peer's [.., y_local, ..] slab (slab exchange). */
+/* Slab-decomposition step 1 with the exchange fused into the last pass (multi-GPU, one process
+ * per GPU). The plan is the LOCAL transform of this rank's slab, e.g. batch = local z planes,
+ * dims = (Y, X). All passes but the last run normally (d_in -> d_work, in place on d_work; d_work
+ * may equal d_in, which then gets overwritten). The last pass transforms axis 0 (Y), the axis being
+ * re-split across ranks, and stores output row y of local plane z straight into
+ *     peer_out[y / (Y/npeers)] [ ((my_rank * batch + z) * (Y/npeers) + y % (Y/npeers)) * X + x ]
+ * i.e. into the [Z][Y/npeers][X] slab of the rank that owns row y. With peer_out[] mapped over
+ * NVLink (b200fft_ipc_open) the all-to-all happens inside the kernel's stores; with local
+ * pointers it is the pack step of an NCCL all-to-all. The caller synchronises the ranks (barrier)
+ * before reading its slab and then runs the Z pass with a plan over (Z, Y/npeers, X), axis_mask=1. */
 B200FFT_API int b200fft_exec_scatter(b200fft_plan* plan, void* const* peer_out, int npeers, int my_rank,
-                         const void* d_in, void* cu_stream);
+                                     const void* d_in, void* d_work, void* cu_stream);
+
+/* Device buffers that can be shared with the other ranks of the node (cudaMalloc + CUDA IPC). */
+#define B200FFT_IPC_HANDLE_BYTES 64
+B200FFT_API int b200fft_malloc(void** d_ptr, size_t bytes);
+B200FFT_API int b200fft_free(void* d_ptr);
+B200FFT_API int b200fft_ipc_export(void* d_ptr, unsigned char handle[B200FFT_IPC_HANDLE_BYTES]);
+B200FFT_API int b200fft_ipc_open(const unsigned char handle[B200FFT_IPC_HANDLE_BYTES], void** d_ptr);
+B200FFT_API int b200fft_ipc_close(void* d_ptr);
 
 B200FFT_API int b200fft_plan_destroy(b200fft_plan* plan);
 

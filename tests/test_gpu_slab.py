@@ -1,0 +1,54 @@
+"""Slab decomposition on ONE GPU: G virtual ranks emulated in one process (their slabs all live on
+cuda:0), exercising b200fft_exec_scatter's peer indexing for G > 1 and the Z pass, against numpy.
+The real multi-process / multi-GPU run is tools/slab_check.py (torchrun, NCCL + CUDA IPC)."""
+import numpy as np
+import pytest
+
+import b200fft
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dims,G", [((64, 64, 64), 2), ((128, 128, 64), 4), ((64, 128, 128), 8), ((512, 512, 16), 2),
+                                    ((64, 64, 64), 1)])
+def test_exec_scatter_virtual_ranks(dims, G):
+    import torch
+    Z, Y, X = dims
+    zl, yl = Z // G, Y // G
+    g = torch.Generator(device="cuda").manual_seed(3)
+    full = torch.randn((Z, Y, X, 2), generator=g, device="cuda")
+    recv = [torch.full((Z, yl, X, 2), float("nan"), device="cuda") for _ in range(G)]
+    plan2d = b200fft.plan_fft("float32", "float32", (zl, Y, X, 2), (zl, Y, X, 2))
+    planz = b200fft.plan_fft("float32", "float32", (1, Z, yl, X, 2), (1, Z, yl, X, 2), axis_mask=1)
+    work = torch.empty((zl, Y, X, 2), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(G):
+        x_local = full[r * zl:(r + 1) * zl].contiguous()
+        keep = x_local.clone()
+        plan2d.exec_scatter(recv, r, x_local, work, st)
+        assert torch.equal(x_local, keep)          # input untouched when d_work != d_in
+    for r in range(G):
+        b200fft.fft(recv[r].unsqueeze(0), recv[r].unsqueeze(0), plan=planz)
+    torch.cuda.synchronize()
+    want = torch.fft.fftn(torch.view_as_complex(full.double().contiguous()))
+    for r in range(G):
+        got = torch.view_as_complex(recv[r].double().contiguous())
+        ref = want[:, r * yl:(r + 1) * yl, :]
+        assert torch.isfinite(recv[r]).all()
+        assert float((got - ref).norm() / ref.norm()) < 2e-6
+
+
+def test_exec_scatter_errors():
+    import torch
+    plan = b200fft.plan_fft("float32", "float32", (4, 64, 64, 2), (4, 64, 64, 2))
+    x = torch.zeros((4, 64, 64, 2), device="cuda")
+    w = torch.zeros_like(x)
+    with pytest.raises(b200fft.B200FFTError):            # 64 rows cannot be split over 3 peers
+        plan.exec_scatter([x, x, x], 0, x, w)
+    with pytest.raises(b200fft.B200FFTError):            # rank outside the peer list
+        plan.exec_scatter([x, x], 2, x, w)
+    rows = b200fft.plan_fft("float32", "float32", (4, 64, 2), (4, 64, 2))
+    x1 = torch.zeros((4, 64, 2), device="cuda")
+    with pytest.raises(b200fft.B200FFTError) as e:       # contiguous-axis pass has no scattering store
+        rows.exec_scatter([x1, x1], 0, x1, torch.zeros_like(x1))
+    assert e.value.status == 4

@@ -1,0 +1,94 @@
+#!/usr/bin/env python3
+"""torchrun entry: slab-decomposed 3-D FFT across the node's GPUs, both exchange modes.
+
+    python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/slab_check.py [--n 512]
+
+1. correctness at 128^3: every rank's Y slab vs torch.fft.fftn of the gathered volume (rank 0 prints)
+2. timing at N^3 (default 512): K calls bracketed by barriers, CUDA events, max over ranks,
+   for exchange = p2p (fused scattering store over CUDA IPC / NVLink) and nccl (pack + all_to_all_single).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "hackathon-fft_b200", "python")]
+import torch
+import torch.distributed as dist
+
+from b200fft.slab import SlabFFT3D
+
+
+def check(n, mode, rank, world):
+    zl, yl = n // world, n // world
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    x = torch.randn((zl, n, n, 2), generator=g, device="cuda")
+    slab = SlabFFT3D((n, n, n), exchange=mode)
+    out = slab.forward(x).clone()
+    out2 = slab.forward(x).clone()      # second call uses the other receive slab
+    full = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(full, x)
+    vol = torch.cat(full, 0)
+    want = torch.fft.fftn(torch.view_as_complex(vol.double().contiguous()))[:, rank * yl:(rank + 1) * yl, :]
+    got = torch.view_as_complex(out.double().contiguous())
+    err = float((got - want).norm() / want.norm())
+    same = bool(torch.equal(out, out2))
+    errs = [None] * world
+    dist.all_gather_object(errs, (err, same))
+    slab.close()
+    return errs
+
+
+def bench(n, mode, rank, world, steps, warmup):
+    zl = n // world
+    x = torch.randn((zl, n, n, 2), device="cuda")
+    slab = SlabFFT3D((n, n, n), exchange=mode)
+    for _ in range(warmup):
+        slab.forward(x)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        slab.forward(x)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    slab.close()
+    return float(t.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = {"world": world, "n": a.n}
+    for mode in ("nccl", "p2p"):
+        try:
+            res["check128_" + mode] = check(128, mode, rank, world)
+            res["ms_%d_%s" % (a.n, mode)] = bench(a.n, mode, rank, world, a.steps, a.warmup)
+        except Exception as e:  # report, keep going with the other mode
+            res["error_" + mode] = "%s: %s" % (type(e).__name__, e)
+    if rank == 0:
+        import math
+        pts = a.n ** 3
+        for mode in ("nccl", "p2p"):
+            k = "ms_%d_%s" % (a.n, mode)
+            if k in res:
+                res["gflops_" + mode] = 5 * pts * math.log2(pts) / res[k] / 1e6
+        print(json.dumps(res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
