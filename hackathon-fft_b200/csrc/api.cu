@@ -108,6 +108,15 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
     return B200FFT_OK;
   };
 
+  // one persistent kernel for all axes when a fused variant covers the problem (fused_registry.cu)
+  if (!dry) {
+    std::unique_ptr<Pass> fused = make_fused_pass(*plan);
+    if (fused) {
+      plan->passes.push_back(std::move(fused));
+      return B200FFT_OK;
+    }
+  }
+
   if (!p.half) {
     bool first = true;
     for (int axis = last; axis >= 0; --axis) {
@@ -199,6 +208,27 @@ int b200fft_ordered_bases(uint64_t length, const uint32_t* bases, int nbases, ui
 
 int b200fft_default_bases(uint64_t length, int gpu_target, uint32_t* out, int cap) {
   return copy_bases(estimate_best_bases(length, gpu_target != 0), out, cap);
+}
+
+int b200fft_schedule_dry_run(int nphases, const int64_t* phases, int64_t batch, int64_t* segments, int cap) {
+  if (nphases < 1 || nphases > 8 || !phases || batch < 0) return -1;
+  std::vector<SchedPhase> ph((size_t)nphases);
+  for (int p = 0; p < nphases; ++p) {
+    ph[p].tiles_per_transform = phases[4 * p];
+    ph[p].tiles_per_group = phases[4 * p + 1];
+    ph[p].dep_div = phases[4 * p + 2];
+    ph[p].quota = phases[4 * p + 3];
+    if (ph[p].tiles_per_transform < 1 || ph[p].tiles_per_group < 1 || ph[p].dep_div < 1) return -1;
+  }
+  const std::vector<NdSegment> segs = build_schedule(nphases, ph.data(), batch);
+  if (segments)
+    for (size_t i = 0; i < segs.size() && (int)i < cap; ++i) {
+      segments[4 * i] = segs[i].phase;
+      segments[4 * i + 1] = segs[i].first_item;
+      segments[4 * i + 2] = segs[i].first_tile;
+      segments[4 * i + 3] = segs[i].count;
+    }
+  return (int)segs.size();
 }
 
 int b200fft_plan_dry_run(const b200fft_desc* desc, char* buf, size_t cap) {
@@ -300,7 +330,8 @@ int b200fft_exec_scatter(b200fft_plan* plan, void* const* peer_out, int npeers, 
   if (plan->prob.half) return fail(B200FFT_ERR_UNSUPPORTED, "exec_scatter takes a complex plan");
   if (my_rank < 0 || my_rank >= npeers) return fail(B200FFT_ERR_INVALID_ARG, "my_rank %d outside 0..%d", my_rank, npeers);
   if (plan->passes.empty() || plan->passes.back()->axis != 0)
-    return fail(B200FFT_ERR_INVALID_ARG, "exec_scatter: the plan's last pass must transform axis 0 (the split axis)");
+    return fail(B200FFT_ERR_INVALID_ARG, "exec_scatter: the plan's last pass must transform axis 0 (the split axis); "
+                                         "create the plan with B200FFT_FLAG_NO_FUSED");
   DeviceGuard guard(plan->device);
   cudaStream_t st = (cudaStream_t)cu_stream;
   const size_t n = plan->passes.size();

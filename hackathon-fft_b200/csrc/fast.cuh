@@ -74,7 +74,9 @@ struct DenseLayout {
 // ---- global accessors ------------------------------------------------------------------------
 // element (o, i, c) of the tile lives at base[o*so + i*si + c]; rows/columns beyond the valid
 // extent (ragged last tile) read as zero and are not written.
-template <bool REAL>
+// COHERENT: the data may have been written earlier in the SAME kernel by another CTA (fused N-d
+// kernel, fused.cuh): read through L2 (ld.global.cg), never through the non-coherent / L1 path.
+template <bool REAL, bool COHERENT = false>
 struct GlobalSrc {
   const void* __restrict__ base;
   long long so, si;
@@ -82,8 +84,13 @@ struct GlobalSrc {
   __device__ __forceinline__ float2 load(int o, int i, int c) const {
     if (o >= valid_o || c >= valid_c) return make_float2(0.f, 0.f);
     const long long idx = o * so + i * si + c;
-    if constexpr (REAL) return make_float2(__ldg(reinterpret_cast<const float*>(base) + idx), 0.f);
-    else return __ldg(reinterpret_cast<const float2*>(base) + idx);
+    if constexpr (REAL) {
+      const float* p = reinterpret_cast<const float*>(base) + idx;
+      return make_float2(COHERENT ? __ldcg(p) : __ldg(p), 0.f);
+    } else {
+      const float2* p = reinterpret_cast<const float2*>(base) + idx;
+      return COHERENT ? __ldcg(p) : __ldg(p);
+    }
   }
 };
 struct GlobalDst {
@@ -303,22 +310,20 @@ struct HalfArgs {
   float scale;
 };
 
-template <int H, class RL, int C, int NT>
-__global__ void __launch_bounds__(NT) rows_r2c_kernel(const __grid_constant__ HalfArgs a) {
-  extern __shared__ __align__(16) float2 smem_f2[];
+// one tile of C rows: `in` = first real row of the tile viewed as H complex, `out` = first output row
+template <int H, class RL, int C, int NT, bool COHERENT = false>
+__device__ __forceinline__ void r2c_tile(const float2* in, float2* __restrict__ out, const float2* __restrict__ tw,
+                                         const float2* __restrict__ tw2, int valid, float2* smem_f2) {
   constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
   constexpr int BUF = EX > C * H ? EX : C * H;
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + BUF;
   // the last stage writes Z[o][k] densely into the buffer the last exchange did not use
   float2* zbuf = ((RL::count - 1) % 2 == 0) ? buf0 : buf1;
-  const long long row0 = (long long)blockIdx.x * C;
-  const int valid = (int)min((long long)C, a.nrows - row0);
-  GlobalSrc<false> src{reinterpret_cast<const float2*>(a.in) + row0 * H, H, 1, valid, 1};
-  run_axis<RL, H, C, 1, NT, false, RowLayoutN<H>::template type>(src, SmemDst<PlaneLayout<H>>{zbuf}, buf0, buf1, a.tw,
-                                                                 1.f, false);
+  GlobalSrc<false, COHERENT> src{in, H, 1, valid, 1};
+  run_axis<RL, H, C, 1, NT, false, RowLayoutN<H>::template type>(src, SmemDst<PlaneLayout<H>>{zbuf}, buf0, buf1, tw, 1.f,
+                                                                 false);
   __syncthreads();
-  float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + row0 * (H + 1);
   const int total = valid * (H + 1);
   for (int idx = threadIdx.x; idx < total; idx += NT) {
     const int o = idx / (H + 1), k = idx - o * (H + 1);
@@ -326,11 +331,20 @@ __global__ void __launch_bounds__(NT) rows_r2c_kernel(const __grid_constant__ Ha
     float2 zm = zbuf[o * H + (k == 0 ? 0 : H - k)];
     zm.y = -zm.y;
     const float2 s = make_float2(zk.x + zm.x, zk.y + zm.y), d = make_float2(zk.x - zm.x, zk.y - zm.y);
-    const float2 w = __ldg(&a.tw2[k]);
+    const float2 w = __ldg(&tw2[k]);
     const float2 t = cmulf(d, w);  // W * (Z[k] - conj(Z[H-k]))
     // X = (s - i t) / 2
     out[idx] = make_float2(0.5f * (s.x + t.y), 0.5f * (s.y - t.x));
   }
+}
+
+template <int H, class RL, int C, int NT>
+__global__ void __launch_bounds__(NT) rows_r2c_kernel(const __grid_constant__ HalfArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  const long long row0 = (long long)blockIdx.x * C;
+  const int valid = (int)min((long long)C, a.nrows - row0);
+  r2c_tile<H, RL, C, NT>(reinterpret_cast<const float2*>(a.in) + row0 * H,
+                         reinterpret_cast<float2*>(a.out) + row0 * (H + 1), a.tw, a.tw2, valid, smem_f2);
 }
 
 // stage-0 source of the C2R kernel: Z[k] from the staged half spectrum

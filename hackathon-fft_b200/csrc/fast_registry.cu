@@ -46,6 +46,8 @@ void register_all() {
   register_cols_tma();
 }
 
+}  // namespace
+
 // can `target` (super-stage radices) be formed by partitioning `ordered` (the user's stage
 // list) into groups with exactly those products?
 bool can_group(std::vector<uint32_t> ordered, std::vector<int> target) {
@@ -120,6 +122,8 @@ std::vector<std::vector<uint32_t>> drop_factor_two(const std::vector<uint32_t>& 
   }
   return out;
 }
+
+namespace {
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {

@@ -35,6 +35,12 @@ struct Variant {
 
 std::vector<Variant>& registry();
 
+// shared with the fused N-d registry (fused_registry.cu)
+bool can_group(std::vector<uint32_t> ordered, std::vector<int> target);
+std::vector<float2> build_twiddles(const std::vector<int>& radices, bool inverse);
+std::vector<float2> build_half_twiddles(long long n, bool inverse);
+std::vector<std::vector<uint32_t>> drop_factor_two(const std::vector<uint32_t>& ordered);
+
 
 // FULL variants instantiate forward/inverse x complex/real-input; tuning candidates only
 // forward complex (they are skipped for other requests).

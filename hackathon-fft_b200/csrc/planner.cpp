@@ -196,4 +196,36 @@ int validate(const b200fft_desc* d, Problem* out) {
   return B200FFT_OK;
 }
 
+std::vector<NdSegment> build_schedule(int nphases, const SchedPhase* ph, long long batch) {
+  std::vector<NdSegment> segs;
+  std::vector<long long> prog(nphases, 0), total(nphases, 0);
+  for (int p = 0; p < nphases; ++p) total[p] = ph[p].tiles_per_transform * batch;
+  long long item = 0;
+  while (true) {
+    bool done = true;
+    for (int p = 0; p < nphases; ++p) done = done && prog[p] == total[p];
+    if (done) break;
+    const std::vector<long long> before(prog);  // what earlier rounds handed out
+    bool any = false;
+    for (int p = 0; p < nphases; ++p) {
+      long long limit = total[p];
+      if (p > 0) {
+        const long long groups_done =
+            before[p - 1] == total[p - 1] ? (total[p] + ph[p].dep_div - 1) / ph[p].dep_div  // ragged last group
+                                          : before[p - 1] / ph[p - 1].tiles_per_group;
+        limit = std::min(limit, groups_done * ph[p].dep_div);
+      }
+      long long n = limit - prog[p];
+      if (ph[p].quota > 0) n = std::min(n, ph[p].quota);
+      if (n <= 0) continue;
+      segs.push_back(NdSegment{p, 0, item, prog[p], n});
+      prog[p] += n;
+      item += n;
+      any = true;
+    }
+    if (!any) break;  // cannot happen for consistent phase descriptions; avoids an endless loop on bad input
+  }
+  return segs;
+}
+
 }  // namespace b200fft

@@ -37,6 +37,27 @@ struct Problem {
   size_t in_elem = 0, out_elem = 0;  // bytes per scalar
 };
 
+// ---- tile schedule of the fused N-d kernel (fused.cuh) ---------------------------------------------
+// A run of consecutive work items that are consecutive tiles of one phase.
+struct NdSegment {
+  int phase;
+  int pad;
+  long long first_item;  // position of the first item in the global order
+  long long first_tile;  // its global tile index: transform * tiles_per_transform + tile
+  long long count;
+};
+struct SchedPhase {
+  long long tiles_per_transform = 0;
+  long long tiles_per_group = 0;  // tiles of this phase per dependency group it completes (unused for the last phase)
+  long long dep_div = 1;          // tile j of this phase needs group j / dep_div of the previous phase (unused for phase 0)
+  long long quota = 0;            // max tiles handed out per pipeline round (0 = everything that is ready)
+};
+// Orders all tiles of `batch` transforms as a software pipeline: round r hands out, for every phase in
+// turn, the tiles whose dependency groups were completely handed out in EARLIER rounds (so a consumer
+// never precedes, and in steady state never closely follows, its producers). Returns the segments in
+// order; every tile of every phase appears exactly once.
+std::vector<NdSegment> build_schedule(int nphases, const SchedPhase* phases, long long batch);
+
 // Mirrors _check_layout_conditions_nd + the bases asserts. Returns a status code
 // and leaves the detail in last_error().
 int validate(const b200fft_desc* d, Problem* out);

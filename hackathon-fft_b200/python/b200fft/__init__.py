@@ -17,12 +17,12 @@ import ctypes
 import os
 
 __all__ = ["plan_fft", "fft", "Plan", "B200FFTError", "ordered_bases", "default_bases", "dry_run",
-           "launch_count", "lib_path", "REAL_FULL", "REAL_HALF", "FLAG_FORCE_GENERIC", "FLAG_NO_CHUNKING"]
+           "launch_count", "lib_path", "REAL_FULL", "REAL_HALF", "FLAG_FORCE_GENERIC", "FLAG_NO_CHUNKING", "FLAG_NO_FUSED"]
 
 MAX_RANK = 8
 U8, F32, F64 = 0, 1, 2
 REAL_FULL, REAL_HALF = 0, 1
-FLAG_FORCE_GENERIC, FLAG_NO_CHUNKING = 1, 2
+FLAG_FORCE_GENERIC, FLAG_NO_CHUNKING, FLAG_NO_FUSED = 1, 2, 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libb200fft.so"))
@@ -76,6 +76,8 @@ SYMBOLS = [
     ("b200fft_ordered_bases", ctypes.c_int, [ctypes.c_uint64, _u32p, ctypes.c_int, _u32p, ctypes.c_int]),
     ("b200fft_default_bases", ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, _u32p, ctypes.c_int]),
     ("b200fft_plan_dry_run", ctypes.c_int, [ctypes.POINTER(_Desc), ctypes.c_char_p, ctypes.c_size_t]),
+    ("b200fft_schedule_dry_run", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int64,
+                                                 ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     ("b200fft_strerror", ctypes.c_char_p, [ctypes.c_int]),
     ("b200fft_last_error", ctypes.c_char_p, []),
     ("b200fft_version", ctypes.c_int, []),
@@ -158,6 +160,19 @@ def default_bases(length, target="gpu"):
     out = (ctypes.c_uint32 * 64)()
     n = lib().b200fft_default_bases(length, 1 if target == "gpu" else 0, out, 64)
     return [int(out[i]) for i in range(n)]
+
+
+def schedule(phases, batch):
+    """Tile schedule of the fused N-d kernel for phases = [(tiles_per_transform, tiles_per_group, dep_div, quota)...]:
+    list of (phase, first_item, first_tile, count) segments (host logic only)."""
+    flat = [int(v) for ph in phases for v in ph]
+    arr = (ctypes.c_int64 * len(flat))(*flat)
+    n = lib().b200fft_schedule_dry_run(len(phases), arr, batch, None, 0)
+    if n < 0:
+        raise B200FFTError(1, "inconsistent phase description")
+    out = (ctypes.c_int64 * (4 * max(1, n)))()
+    lib().b200fft_schedule_dry_run(len(phases), arr, batch, out, n)
+    return [tuple(int(out[4 * i + k]) for k in range(4)) for i in range(n)]
 
 
 def launch_count():

@@ -52,7 +52,8 @@ class CudaSlabEngine:
     def __init__(self, dims, world, inverse=False):
         Z, Y, X = dims
         self.zl, self.yl = Z // world, Y // world
-        self.plan2d = b200fft.plan_fft("float32", "float32", (self.zl, Y, X, 2), (self.zl, Y, X, 2), inverse=inverse)
+        self.plan2d = b200fft.plan_fft("float32", "float32", (self.zl, Y, X, 2), (self.zl, Y, X, 2), inverse=inverse,
+                                       flags=b200fft.FLAG_NO_FUSED)  # exec_scatter drives the per-axis passes
         self.planz = b200fft.plan_fft("float32", "float32", (1, Z, self.yl, X, 2), (1, Z, self.yl, X, 2),
                                       axis_mask=1, inverse=inverse)
         self.work = torch.empty((self.zl, Y, X, 2), device="cuda", dtype=torch.float32)

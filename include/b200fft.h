@@ -69,7 +69,10 @@ enum {
      role of the reference's `_test: _GPUTest` path forcer, _ndim_fft_gpu.mojo:453-459). */
   B200FFT_FLAG_FORCE_GENERIC = 1u << 0,
   /* Disable L2-resident chunking of multi-pass N-d transforms. */
-  B200FFT_FLAG_NO_CHUNKING = 1u << 1
+  B200FFT_FLAG_NO_CHUNKING = 1u << 1,
+  /* Never use the fused N-d kernel (one persistent kernel for all axes, intermediate kept in L2):
+     run one kernel per axis instead. b200fft_exec_scatter needs per-axis passes. */
+  B200FFT_FLAG_NO_FUSED = 1u << 2
 };
 
 /*
@@ -156,6 +159,13 @@ B200FFT_API int b200fft_ordered_bases(uint64_t length, const uint32_t* bases, in
 B200FFT_API int b200fft_default_bases(uint64_t length, int gpu_target, uint32_t* out, int cap);
 /* validate a descriptor and write the pass list it would produce, without touching CUDA */
 B200FFT_API int b200fft_plan_dry_run(const b200fft_desc* desc, char* buf, size_t cap);
+
+/* Tile schedule of the fused N-d kernel (host logic, no CUDA): phases[p] = {tiles_per_transform,
+ * tiles_per_group, dep_div, quota}; writes up to `cap` segments as {phase, first_item, first_tile, count}
+ * and returns the number of segments (or -1). Tests use it to check that every tile appears once and
+ * never before the tiles it depends on. */
+B200FFT_API int b200fft_schedule_dry_run(int nphases, const int64_t* phases /* [nphases][4] */, int64_t batch,
+                                         int64_t* segments /* [cap][4] */, int cap);
 
 /* ---- errors / bookkeeping */
 B200FFT_API const char* b200fft_strerror(int status);

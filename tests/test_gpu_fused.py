@@ -1,0 +1,133 @@
+"""Fused N-d kernel (one persistent kernel for all axes, intermediate kept in L2) against torch float64
+FFTs and against the per-axis passes of the same library, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import b200fft
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _enable_fused(monkeypatch):
+    monkeypatch.setenv("B200FFT_FUSED", "1")   # opt-in while the per-axis kernels are faster
+
+REL_L2 = 2e-6          # ours vs float64, N(0,1) data (x sqrt(ndims) margin included)
+MAX_ABS = 1e-5
+
+
+def _ref(x, inverse=False, half=False):
+    import torch
+    if x.shape[-1] == 1:
+        xd = x[..., 0].double()
+        axes = tuple(range(1, xd.dim()))
+        return torch.fft.rfftn(xd, dim=axes) if half else torch.fft.fftn(xd, dim=axes)
+    xc = torch.view_as_complex(x.double().contiguous())
+    axes = tuple(range(1, xc.dim()))
+    return torch.fft.ifftn(xc, dim=axes) if inverse else torch.fft.fftn(xc, dim=axes)
+
+
+def _check(out, want):
+    import torch
+    got = torch.view_as_complex(out.double().contiguous())
+    rel = float((got - want).norm() / want.norm())
+    mx = float((got - want).abs().max() / want.abs().max())
+    assert rel < REL_L2 and mx < MAX_ABS, (rel, mx)
+
+
+CASES = [
+    # (shape incl. batch, inverse, mode, preferred variant substring or None)
+    ((5, 64, 64, 64), False, "c2c", "plane"),
+    ((5, 64, 64, 64), True, "c2c", "plane"),
+    ((23, 64, 64, 64), False, "c2c", "rows"),
+    ((3, 128, 128, 128), False, "c2c", "plane"),
+    ((2, 128, 128, 128), True, "c2c", "rows"),
+    ((1, 256, 256, 256), False, "c2c", None),
+    ((2, 256, 256, 256), True, "c2c", None),
+    ((1, 512, 512, 512), False, "c2c", None),
+    ((7, 640, 480), False, "c2c", None),
+    ((3, 640, 480), True, "c2c", None),
+    ((5, 640, 480), False, "real", None),
+    ((5, 640, 480), False, "half", None),
+    ((1, 640, 480), False, "c2c", None),
+]
+
+
+@pytest.mark.parametrize("shape,inverse,mode,prefer", CASES)
+def test_fused_matches_float64_and_per_axis_passes(shape, inverse, mode, prefer, monkeypatch):
+    import torch
+    if prefer:
+        monkeypatch.setenv("B200FFT_FUSED_PREFER", prefer)
+    comps = 2 if mode == "c2c" else 1
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(tuple(shape) + (comps,), generator=g, device="cuda")
+    oshape = tuple(shape[:-1]) + (shape[-1] // 2 + 1, 2) if mode == "half" else tuple(shape) + (2,)
+    rm = b200fft.REAL_HALF if mode == "half" else b200fft.REAL_FULL
+    plan = b200fft.plan_fft("float32", "float32", x.shape, oshape, inverse=inverse, real_mode=rm)
+    assert plan.describe().startswith("fused"), plan.describe()
+    if prefer:
+        assert prefer in plan.describe()
+    assert plan.launches == 1
+    out = torch.full(oshape, float("nan"), device="cuda")
+    keep = x.clone()
+    b200fft.fft(out, x, plan=plan)
+    torch.cuda.synchronize()
+    assert torch.equal(x, keep)
+    want = _ref(x, inverse, mode == "half")
+    _check(out, want)
+    # a second and third launch reuse the self-clearing counters
+    out2 = torch.full(oshape, float("nan"), device="cuda")
+    b200fft.fft(out2, x, plan=plan)
+    b200fft.fft(out2, x, plan=plan)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    # the per-axis passes of the same library give the same result up to rounding order
+    plain = b200fft.plan_fft("float32", "float32", x.shape, oshape, inverse=inverse, real_mode=rm,
+                             flags=b200fft.FLAG_NO_FUSED)
+    assert not plain.describe().startswith("fused")
+    out3 = torch.empty(oshape, device="cuda")
+    b200fft.fft(out3, x, plan=plain)
+    torch.cuda.synchronize()
+    assert float((out3 - out).norm() / out.norm()) < 1e-6
+    plan.destroy()
+    plain.destroy()
+
+
+def test_fused_in_place():
+    import torch
+    x = torch.randn((6, 64, 64, 64, 2), device="cuda")
+    want = _ref(x)
+    plan = b200fft.plan_fft("float32", "float32", x.shape, x.shape)
+    assert plan.describe().startswith("fused")
+    b200fft.fft(x, x, plan=plan)
+    torch.cuda.synchronize()
+    _check(x, want)
+
+
+def test_fused_respects_user_bases_and_opt_out(monkeypatch):
+    import torch
+    x = torch.randn((2, 64, 64, 64, 2), device="cuda")
+    # [4] x3 can be grouped into the variant's (8)(8)? 4*4*4 = 64 -> groups of product 8 do not exist
+    p = b200fft.plan_fft("float32", "float32", x.shape, x.shape, bases=[[4], [2], [2]])
+    assert not p.describe().startswith("fused")
+    out = torch.empty_like(x)
+    b200fft.fft(out, x, plan=p)
+    torch.cuda.synchronize()
+    _check(out, _ref(x))
+    monkeypatch.setenv("B200FFT_FUSED", "0")
+    p2 = b200fft.plan_fft("float32", "float32", x.shape, x.shape)
+    assert not p2.describe().startswith("fused")
+
+
+def test_fused_through_exec_host():
+    """exec_host runs the fused kernel on batch chunks (a schedule per chunk size)."""
+    import torch
+    x = torch.randn((20, 64, 64, 64, 2))
+    h_in = x.pin_memory()
+    h_out = torch.empty_like(x).pin_memory()
+    plan = b200fft.plan_fft("float32", "float32", x.shape, x.shape)
+    plan.exec_host(h_out.numpy(), h_in.numpy())
+    want = _ref(x.cuda())
+    _check(h_out.cuda(), want)
