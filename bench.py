@@ -286,6 +286,48 @@ def bench_shape(name, shape, real_in, torch, b200fft, steps, warmup, peak):
     return row
 
 
+def bench_slab(n, world, rank, torch, dist, steps=10, warmup=3):
+    """Single n^3 C2C transform slab-decomposed over the ranks (b200fft.slab.SlabFFT3D): local 2-D FFTs,
+    exchange (fused into the Y pass's stores over NVLink = "p2p", or pack + NCCL all-to-all = "nccl"), Z pass.
+    Timed with CUDA events between barriers, max over ranks, exchange included; output stays Y-slab distributed."""
+    from b200fft.slab import SlabFFT3D
+    res = {"n": n, "ranks": world, "output": "Y-slab distributed (transposed out)", "timed": "2-D pass + exchange + Z pass"}
+    if n % world:
+        res["error"] = "%d not divisible by %d ranks" % (n, world)
+        return res
+    zl = n // world
+    g = torch.Generator(device="cuda").manual_seed(77 + rank)
+    x = torch.randn((zl, n, n, 2), generator=g, device="cuda")
+    for mode in ("p2p", "nccl"):
+        try:
+            sl = SlabFFT3D((n, n, n), exchange=mode)
+            for _ in range(warmup):
+                sl.forward(x)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = sl.forward(x)
+            e1.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            # parity: energy (Parseval) of the distributed result against the input, reduced over ranks
+            e = torch.stack([out.double().pow(2).sum(), x.double().pow(2).sum()])
+            dist.all_reduce(e)
+            res[mode] = {"ms": ms, "gflops": 5.0 * n ** 3 * math.log2(n ** 3) / ms / 1e6,
+                         "parseval_rel_err": abs(float(e[0] / (e[1] * n ** 3)) - 1.0)}
+            sl.close()
+            del out
+        except Exception as ex:  # report, keep the bench line
+            res[mode] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -373,6 +415,12 @@ def main():
            "h2d_bytes_per_step": plan.in_bytes, "d2h_bytes_per_step": plan.out_bytes,
            "matches_device_path": e2e_ok, "api": "b200fft_exec_host (pinned host buffers, chunked 3-stream pipeline)"}
 
+    # ---- N > 1: the single 512^3 transform, slab-decomposed over the ranks (exchange inside the timed region)
+    slab = None
+    if dist:
+        del h_in, h_out
+        slab = bench_slab(512, world, rank, torch, dist)
+
     if rank != 0:
         if dist:
             dist.barrier()
@@ -381,10 +429,10 @@ def main():
 
     ab = algorithmic_bytes(shape)
     kernel_ms = ms / max(1, plan.launches)
-    traffic = None
+    traffic = None  # ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(PRIMARY["name"])
+            traffic = json.load(f).get(PRIMARY["name"], {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": ab / plan.launches / kernel_ms / 1e6, "peak": peak, "unit": "GB/s",
@@ -412,7 +460,9 @@ def main():
                    "flop_model": "5*N*log2(N) per transform"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
-    del x, out, h_in, h_out
+    if slab is not None:
+        line["slab_3d_1x512x512x512"] = slab
+    del x, out
     plan.destroy()
     torch.cuda.empty_cache()
 

@@ -385,10 +385,12 @@ int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in) {
   const size_t in_stride = (size_t)p.in_scalars_per_batch * p.in_elem;
   const size_t out_stride = (size_t)p.out_scalars_per_batch * p.out_elem;
   if (!plan->host_ready) {
-    // ~8 chunks, at least 1 batch item each, at most 256 MiB of output per chunk
-    int64_t chunk = std::max<int64_t>(1, (p.batch + 7) / 8);
-    const size_t cap = (size_t)256 << 20;
-    while (chunk > 1 && (size_t)chunk * std::max(in_stride, out_stride) > cap) chunk = (chunk + 1) / 2;
+    // chunks of ~24 MiB (fill / drain of the 3-stage pipeline costs one chunk each way), at least 4 and
+    // at most 64 of them, at least 1 batch item each
+    const size_t per = std::max(in_stride, out_stride);
+    int64_t nchunks = (int64_t)(((size_t)p.batch * per + ((size_t)24 << 20) - 1) / ((size_t)24 << 20));
+    nchunks = std::min<int64_t>(64, std::max<int64_t>(4, nchunks));
+    int64_t chunk = std::max<int64_t>(1, (p.batch + nchunks - 1) / nchunks);
     if (plan->chunk_batches > 0) chunk = ((chunk + plan->chunk_batches - 1) / plan->chunk_batches) * plan->chunk_batches;
     plan->host_chunk = chunk;
     for (int i = 0; i < 3; ++i) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->hs[i], cudaStreamNonBlocking));
