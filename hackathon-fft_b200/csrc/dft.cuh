@@ -93,8 +93,36 @@ struct Tw {
 };
 
 // ---- complex helpers --------------------------------------------------------------------
-B200_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-B200_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// With B200FFT_PACKED (defined per translation unit, before this header): complex add / subtract as ONE
+// packed instruction on sm_100a (add.rn.f32x2 -> FADD2 on a 64-bit register pair; same IEEE rounding as
+// two scalar adds). Radix-2^k butterflies are ~2/3 complex adds, so this removes about a quarter of all
+// issued instructions: FADD 27.7k -> 2.0k + 13.4k FADD2 in the pow2 row kernels' SASS. Measured on B200
+// (profiles/r1_packed_fadd2.md) it HURTS the HBM-bound contiguous pow2 kernels (128: 0.151 -> 0.191 ms,
+// 1024: 0.237 -> 0.306 ms: FADD2 issues slower than the two FADDs it replaces, which dual-issue across the
+// fma/alu pipes) and helps the issue-bound strided / mixed-radix ones (512^3: 1.11 -> 1.005 ms), so it is
+// enabled only in the translation units where it wins.
+B200_HD float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && defined(B200FFT_PACKED)
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+B200_HD float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && defined(B200FFT_PACKED)
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 B200_HD float2 cmulf(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
 // multiply by -i (forward direction) / +i (inverse): the quarter-turn twiddle
 template <bool INV>

@@ -113,9 +113,29 @@ struct SmemDst {
   __device__ __forceinline__ void store(int o, int i, int c, float2 v) const { buf[Layout::off(o, i, c)] = v; }
 };
 
+// barrier between the stages of a tile: the whole CTA, or (NB) only the NT consumer threads of a
+// warp-specialised kernel (named barrier 1; the producer warp never joins it)
+template <int NT, bool NB>
+__device__ __forceinline__ void tile_sync() {
+  if constexpr (NB) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+  else __syncthreads();
+}
+
 // ---- one Stockham stage over a tile -------------------------------------------------------------
 // tw points at this stage's table: tw[(j-1)*P + p] = W_{P*R}^{j*p} (conjugated for inverse).
-template <int R, int P, int N, int O, int CN, int NT, bool INV, class Src, class Dst>
+// TWS: `tw` points into shared memory (persistent kernels stage their tables once per CTA)
+template <bool TWS>
+__device__ __forceinline__ float2 tw_load(const float2* tw, int idx) {
+  if constexpr (TWS) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(tw + idx)));
+    return v;
+  } else {
+    return __ldg(tw + idx);
+  }
+}
+
+template <int R, int P, int N, int O, int CN, int NT, bool INV, bool TWS = false, class Src, class Dst>
 __device__ __forceinline__ void run_stage(const Src& src, const Dst& dst, const float2* __restrict__ tw, float scale,
                                           bool do_scale) {
   constexpr int NB = N / R;  // butterflies per transform
@@ -136,7 +156,7 @@ __device__ __forceinline__ void run_stage(const Src& src, const Dst& dst, const 
       for (int j = 0; j < R; ++j) x[j] = src.load(o, n + j * NB, c);
       if constexpr (P > 1) {
 #pragma unroll
-        for (int j = 1; j < R; ++j) x[j] = cmulf(x[j], __ldg(&tw[(j - 1) * P + p]));
+        for (int j = 1; j < R; ++j) x[j] = cmulf(x[j], tw_load<TWS>(tw, (j - 1) * P + p));
       }
       Dft<R, INV>::run(x);
       if (do_scale) {
@@ -170,7 +190,7 @@ struct PlaneLayout {
 // (after stage e) goes through buffer (E0 + e) % 2. LayoutFor<Q, P> gives the exchange layout
 // after a stage with those parameters.
 template <class RL, int N, int O, int CN, int NT, bool INV, template <int, int> class LayoutFor, int E0 = 0, int S = 0,
-          class Src, class GDst>
+          bool NB = false, bool TWS = false, class Src, class GDst>
 __device__ __forceinline__ void run_axis(const Src& src, const GDst& gdst, float2* buf0, float2* buf1,
                                          const float2* __restrict__ tw, float scale, bool do_scale) {
   constexpr int R = RL::r[S];
@@ -178,13 +198,13 @@ __device__ __forceinline__ void run_axis(const Src& src, const GDst& gdst, float
   constexpr bool last = (S == RL::count - 1);
   const float2* tws = tw + RL::tw_offset(S);
   if constexpr (last) {
-    run_stage<R, P, N, O, CN, NT, INV>(src, gdst, tws, scale, do_scale);
+    run_stage<R, P, N, O, CN, NT, INV, TWS>(src, gdst, tws, scale, do_scale);
   } else {
     using L = LayoutFor<P * R, P>;
     float2* buf = ((E0 + S) % 2 == 0) ? buf0 : buf1;
-    run_stage<R, P, N, O, CN, NT, INV>(src, SmemDst<L>{buf}, tws, 1.f, false);
-    __syncthreads();
-    run_axis<RL, N, O, CN, NT, INV, LayoutFor, E0, S + 1>(SmemSrc<L>{buf}, gdst, buf0, buf1, tw, scale, do_scale);
+    run_stage<R, P, N, O, CN, NT, INV, TWS>(src, SmemDst<L>{buf}, tws, 1.f, false);
+    tile_sync<NT, NB>();
+    run_axis<RL, N, O, CN, NT, INV, LayoutFor, E0, S + 1, NB, TWS>(SmemSrc<L>{buf}, gdst, buf0, buf1, tw, scale, do_scale);
   }
 }
 
@@ -310,20 +330,30 @@ struct HalfArgs {
   float scale;
 };
 
-// one tile of C rows: `in` = first real row of the tile viewed as H complex, `out` = first output row
-template <int H, class RL, int C, int NT, bool COHERENT = false>
-__device__ __forceinline__ void r2c_tile(const float2* in, float2* __restrict__ out, const float2* __restrict__ tw,
-                                         const float2* __restrict__ tw2, int valid, float2* smem_f2) {
+// one tile of C rows: `src` yields the real rows viewed as H complex each, `out` = first output row.
+// `after_stage0` runs once the input has been consumed (async kernels release their input buffer there).
+template <int H, class RL, int C, int NT, bool NB = false, bool TWS = false, class Src, class Hook>
+__device__ __forceinline__ void r2c_tile_from(const Src& src, float2* __restrict__ out, const float2* __restrict__ tw,
+                                              const float2* __restrict__ tw2, int valid, float2* smem_f2, Hook after_stage0) {
   constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
   constexpr int BUF = EX > C * H ? EX : C * H;
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + BUF;
   // the last stage writes Z[o][k] densely into the buffer the last exchange did not use
   float2* zbuf = ((RL::count - 1) % 2 == 0) ? buf0 : buf1;
-  GlobalSrc<false, COHERENT> src{in, H, 1, valid, 1};
-  run_axis<RL, H, C, 1, NT, false, RowLayoutN<H>::template type>(src, SmemDst<PlaneLayout<H>>{zbuf}, buf0, buf1, tw, 1.f,
-                                                                 false);
-  __syncthreads();
+  if constexpr (RL::count == 1) {
+    run_stage<RL::r[0], 1, H, C, 1, NT, false>(src, SmemDst<PlaneLayout<H>>{zbuf}, tw, 1.f, false);
+    tile_sync<NT, NB>();
+    after_stage0();
+  } else {
+    using L0 = typename RowLayoutN<H>::template type<RL::r[0], 1>;
+    run_stage<RL::r[0], 1, H, C, 1, NT, false>(src, SmemDst<L0>{buf0}, tw, 1.f, false);
+    tile_sync<NT, NB>();
+    after_stage0();
+    run_axis<RL, H, C, 1, NT, false, RowLayoutN<H>::template type, 0, 1, NB, TWS>(SmemSrc<L0>{buf0}, SmemDst<PlaneLayout<H>>{zbuf},
+                                                                            buf0, buf1, tw, 1.f, false);
+    tile_sync<NT, NB>();
+  }
   const int total = valid * (H + 1);
   for (int idx = threadIdx.x; idx < total; idx += NT) {
     const int o = idx / (H + 1), k = idx - o * (H + 1);
@@ -336,6 +366,12 @@ __device__ __forceinline__ void r2c_tile(const float2* in, float2* __restrict__ 
     // X = (s - i t) / 2
     out[idx] = make_float2(0.5f * (s.x + t.y), 0.5f * (s.y - t.x));
   }
+}
+template <int H, class RL, int C, int NT, bool COHERENT = false>
+__device__ __forceinline__ void r2c_tile(const float2* in, float2* __restrict__ out, const float2* __restrict__ tw,
+                                         const float2* __restrict__ tw2, int valid, float2* smem_f2) {
+  GlobalSrc<false, COHERENT> src{in, H, 1, valid, 1};
+  r2c_tile_from<H, RL, C, NT, false>(src, out, tw, tw2, valid, smem_f2, [] {});
 }
 
 template <int H, class RL, int C, int NT>

@@ -1,4 +1,5 @@
 // Strided-axis variants, power-of-two lengths: <N, columns per CTA, threads, FULL, super-stages...>
+#define B200FFT_PACKED 1  // packed FADD2 complex adds: measured win for these kernels (dft.cuh)
 #include "fast_registry.hpp"
 namespace b200fft {
 void register_cols_pow2() {

@@ -1,4 +1,5 @@
 // Contiguous-row variants, mixed-radix lengths: <N, rows per CTA, threads, FULL, super-stages...>
+#define B200FFT_PACKED 1  // packed FADD2 complex adds: measured win for these kernels (dft.cuh)
 #include "fast_registry.hpp"
 namespace b200fft {
 void register_rows_mixed() {

@@ -123,8 +123,6 @@ std::vector<std::vector<uint32_t>> drop_factor_two(const std::vector<uint32_t>& 
   return out;
 }
 
-namespace {
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
@@ -137,6 +135,8 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   }();
   return fn;
 }
+
+bool tensor_maps_available() { return tensor_map_encoder() != nullptr; }
 
 // tensor map over the (inner, N, outer) view of a dense complex64 array; box = (CW, box_rows, 1)
 bool encode_axis_map(CUtensorMap* map, const void* base, long long inner, long long n, long long outer, int cw,
@@ -151,6 +151,8 @@ bool encode_axis_map(CUtensorMap* map, const void* base, long long inner, long l
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+namespace {
 
 struct FastPass : Pass {
   const Variant* v = nullptr;

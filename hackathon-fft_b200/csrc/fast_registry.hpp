@@ -40,6 +40,11 @@ bool can_group(std::vector<uint32_t> ordered, std::vector<int> target);
 std::vector<float2> build_twiddles(const std::vector<int>& radices, bool inverse);
 std::vector<float2> build_half_twiddles(long long n, bool inverse);
 std::vector<std::vector<uint32_t>> drop_factor_two(const std::vector<uint32_t>& ordered);
+// tensor map over the (inner, n, outer) view of a dense complex64 array, box = (cw, box_rows, 1); false
+// when the driver entry point is unavailable or the encode fails
+bool encode_axis_map(CUtensorMap* map, const void* base, long long inner, long long n, long long outer, int cw,
+                     int box_rows);
+bool tensor_maps_available();
 
 
 // FULL variants instantiate forward/inverse x complex/real-input; tuning candidates only

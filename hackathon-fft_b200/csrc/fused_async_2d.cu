@@ -1,0 +1,13 @@
+// Fused 2-D variants, version 2 (fused2.cuh): rows (last axis) then the strided axis.
+#include "fused_registry.hpp"
+namespace b200fft {
+void register_fused_async_2d() {
+  using R24x20 = Radices<24, 20>;
+  using R32x20 = Radices<32, 20>;
+  using R16x15 = Radices<16, 15>;
+  reg_fused_async<320, 1, ARows<480, R24x20, 8, false, false>, ACols<640, R32x20, 8, false>>({640, 480}, 0);
+  reg_fused_async<320, 1, ARows<480, R24x20, 8, true, false>, ACols<640, R32x20, 8, true>>({640, 480}, 0);
+  reg_fused_async<320, 1, ARows<480, R24x20, 8, false, true>, ACols<640, R32x20, 8, false>>({640, 480}, 1);
+  // half spectrum: 241 columns are not a whole number of tiles -> no v2 variant (v1 covers it)
+}
+}  // namespace b200fft

@@ -1,0 +1,24 @@
+// Fused 3-D variants, version 2 (fused2.cuh: producer warp + bulk-async staging):
+// <consumer threads, min CTAs/SM, phases...>(dims, mode). Order = preference.
+#include "fused_registry.hpp"
+namespace b200fft {
+template <bool INV>
+static void reg3d_async() {
+  using R8x8 = Radices<8, 8>;
+  using R16x8 = Radices<16, 8>;
+  using R16x16 = Radices<16, 16>;
+  using R32x16 = Radices<32, 16>;
+  reg_fused_async<256, 2, APlane<64, 64, R8x8, R8x8, INV>, ACols<64, R8x8, 32, INV>>({64, 64, 64}, 0);
+  reg_fused_async<256, 2, ARows<64, R8x8, 32, INV, false>, ACols<64, R8x8, 32, INV>, ACols<64, R8x8, 32, INV>>({64, 64, 64}, 0);
+  reg_fused_async<256, 2, ARows<128, R16x8, 32, INV, false>, ACols<128, R16x8, 32, INV>, ACols<128, R16x8, 32, INV>>(
+      {128, 128, 128}, 0);
+  reg_fused_async<256, 2, ARows<256, R16x16, 16, INV, false>, ACols<256, R16x16, 16, INV>, ACols<256, R16x16, 16, INV>>(
+      {256, 256, 256}, 0);
+  reg_fused_async<256, 2, ARows<512, R32x16, 8, INV, false>, ACols<512, R32x16, 8, INV>, ACols<512, R32x16, 8, INV>>(
+      {512, 512, 512}, 0);
+}
+void register_fused_async_3d() {
+  reg3d_async<false>();
+  reg3d_async<true>();
+}
+}  // namespace b200fft

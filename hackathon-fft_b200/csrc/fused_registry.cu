@@ -31,6 +31,8 @@ std::vector<FusedVariant>& fused_registry() {
 }
 void register_fused_3d();
 void register_fused_2d();
+void register_fused_async_3d();
+void register_fused_async_2d();
 
 namespace {
 
@@ -38,6 +40,8 @@ void register_all_fused() {
   static bool done = false;
   if (done) return;
   done = true;
+  register_fused_async_3d();  // v2 first: preferred when applicable
+  register_fused_async_2d();
   register_fused_3d();
   register_fused_2d();
 }
@@ -54,6 +58,7 @@ struct FusedPass : Pass {
   SchedPhase sched[ND_MAX_PHASES];
   int groups[ND_MAX_PHASES] = {0, 0, 0};
   int max_grid = 148;
+  struct MapGeom { long long inner = 0, n = 0, outer_per_batch = 0; int cw = 0, box_rows = 0; } geom[ND_MAX_PHASES];
   std::string text;
   struct PerBatch {
     NdSegment* d_segs = nullptr;
@@ -108,7 +113,17 @@ struct FusedPass : Pass {
     for (int p = 0; p < ND_MAX_PHASES; ++p) a.cnt_off[p] = pb->cnt_off[p];
     a.nwords = pb->nwords;
     const unsigned grid = (unsigned)std::min<long long>(pb->total_items, max_grid);
-    v->launch(a, grid, v->smem, stream);
+    if (v->async) {
+      CUtensorMap maps[ND_MAX_PHASES];
+      memset(maps, 0, sizeof maps);
+      for (int q = 1; q < v->nphases; ++q)
+        if (!encode_axis_map(&maps[q], dst, geom[q].inner, geom[q].n, geom[q].outer_per_batch * nbatch, geom[q].cw,
+                             geom[q].box_rows))
+          return fail(B200FFT_ERR_CUDA, "cuTensorMapEncodeTiled failed for phase %d of %s", q, v->name.c_str());
+      v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
+    } else {
+      v->launch(a, grid, v->smem, stream);
+    }
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     B200_CUDA_CHECK(cudaGetLastError());
     return B200FFT_OK;
@@ -179,6 +194,16 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
       if (!ok) continue;
       // group structure: rows tiles must not straddle the next phase's outer slabs
       if ((v.ph[0].kind == ND_ROWS || v.ph[0].kind == ND_R2C) && p.rank == 3 && dims[1] % v.ph[0].tile) continue;
+      if (v.async) {
+        // bulk-async staging: TMA boxes need whole tiles and 16-byte strides on every strided phase
+        if (!tensor_maps_available()) continue;
+        for (int q = 1; q < v.nphases && ok; ++q) {
+          long long inner = 1;
+          for (int a = axes[q] + 1; a < p.rank; ++a) inner *= cdims[a];
+          ok = inner % v.ph[q].tile == 0 && inner % 2 == 0;
+        }
+        if (!ok) continue;
+      }
       pick = &v;
       pick_axes = axes;
       break;
@@ -241,6 +266,11 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
       P.tiles_per_transform = (int)(prod(dims, 0, a) * P.tiles_per_outer);
       P.dep_div = P.tiles_per_outer;
       tile_bytes = (long long)ph.tile * dims[a] * 8;
+      pass->geom[q].inner = P.inner;
+      pass->geom[q].n = dims[a];
+      pass->geom[q].outer_per_batch = prod(dims, 0, a);
+      pass->geom[q].cw = ph.tile;
+      pass->geom[q].box_rows = tma_box_rows((int)dims[a]);
     }
     if (!lastp) {
       // the next phase is a strided pass over axis a' (= the axis left of everything done so far);

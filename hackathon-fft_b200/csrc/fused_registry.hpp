@@ -7,6 +7,7 @@
 
 #include "fast_registry.hpp"
 #include "fused.cuh"
+#include "fused2.cuh"
 
 namespace b200fft {
 
@@ -28,6 +29,9 @@ struct FusedVariant {
   int threads = 0;
   size_t smem = 0;
   void (*launch)(const NdArgs&, unsigned, size_t, cudaStream_t) = nullptr;
+  // v2 (fused2.cuh): producer warp + bulk-async staging; threads = consumers + 32
+  bool async = false;
+  void (*launch_async)(const NdArgs&, const CUtensorMap&, const CUtensorMap&, unsigned, size_t, cudaStream_t) = nullptr;
   const void* func = nullptr;
 };
 
@@ -37,6 +41,14 @@ template <int NT, int MINB, class P0, class P1, class P2>
 struct FusedV {
   static void launch(const NdArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
     nd_fused_kernel<NT, MINB, P0, P1, P2><<<grid, NT, smem, st>>>(a);
+  }
+};
+
+template <int NT, int MINB, class P0, class P1, class P2>
+struct FusedAsyncV {
+  static void launch(const NdArgs& a, const CUtensorMap& m1, const CUtensorMap& m2, unsigned grid, size_t smem,
+                     cudaStream_t st) {
+    nd_async_kernel<NT, MINB, P0, P1, P2><<<grid, NT + 32, smem, st>>>(a, m1, m2);
   }
 };
 
@@ -81,6 +93,30 @@ void reg_fused(std::vector<int> dims, int mode, const char* tag = "") {
   for (size_t i = 0; i < dims.size(); ++i) name += (i ? "x" : "") + std::to_string(dims[i]);
   name += std::string(v.inverse ? "_inv" : "") + (mode == 1 ? "_real" : mode == 2 ? "_r2c" : "") + "_t" + std::to_string(NT) +
           "_" + v.ph[0].text + (tag[0] ? std::string("_") + tag : "");
+  v.name = name;
+  fused_registry().push_back(v);
+}
+
+// v2 variants: <consumer threads, min CTAs per SM, async phase types...>(dims, mode)
+template <int NT, int MINB, class P0, class P1, class P2 = ANone>
+void reg_fused_async(std::vector<int> dims, int mode, const char* tag = "") {
+  FusedVariant v;
+  v.dims = dims;
+  v.inverse = P1::inverse;
+  v.mode = mode;
+  v.nphases = P2::none ? 2 : 3;
+  v.ph[0] = fused_phase_info<P0>();
+  v.ph[1] = fused_phase_info<P1>();
+  v.ph[2] = fused_phase_info<P2>();
+  v.threads = NT + 32;
+  v.smem = nd_async_smem<P0, P1, P2>();
+  v.async = true;
+  v.launch_async = &FusedAsyncV<NT, MINB, P0, P1, P2>::launch;
+  v.func = (const void*)nd_async_kernel<NT, MINB, P0, P1, P2>;
+  std::string name = "ndA";
+  for (size_t i = 0; i < dims.size(); ++i) name += (i ? "x" : "") + std::to_string(dims[i]);
+  name += std::string(v.inverse ? "_inv" : "") + (mode == 1 ? "_real" : mode == 2 ? "_r2c" : "") + "_t" + std::to_string(NT) +
+          "+32_" + v.ph[0].text + (tag[0] ? std::string("_") + tag : "");
   v.name = name;
   fused_registry().push_back(v);
 }

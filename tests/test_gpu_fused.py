@@ -38,28 +38,40 @@ def _check(out, want):
 
 
 CASES = [
-    # (shape incl. batch, inverse, mode, preferred variant substring or None)
-    ((5, 64, 64, 64), False, "c2c", "plane"),
-    ((5, 64, 64, 64), True, "c2c", "plane"),
-    ((23, 64, 64, 64), False, "c2c", "rows"),
-    ((3, 128, 128, 128), False, "c2c", "plane"),
-    ((2, 128, 128, 128), True, "c2c", "rows"),
-    ((1, 256, 256, 256), False, "c2c", None),
-    ((2, 256, 256, 256), True, "c2c", None),
-    ((1, 512, 512, 512), False, "c2c", None),
-    ((7, 640, 480), False, "c2c", None),
-    ((3, 640, 480), True, "c2c", None),
-    ((5, 640, 480), False, "real", None),
-    ((5, 640, 480), False, "half", None),
-    ((1, 640, 480), False, "c2c", None),
+    # (shape incl. batch, inverse, mode, variant-name substring: "ndA" = v2 (producer warp + bulk-async
+    #  staging, fused2.cuh), "nd<dims>" = v1 (fused.cuh))
+    ((5, 64, 64, 64), False, "c2c", "t256_plane"),
+    ((5, 64, 64, 64), True, "c2c", "t256_plane"),
+    ((23, 64, 64, 64), False, "c2c", "t256_rows"),
+    ((3, 128, 128, 128), False, "c2c", "t512_plane"),
+    ((2, 128, 128, 128), True, "c2c", "nd128x128x128_inv_t256_rows"),
+    ((1, 256, 256, 256), False, "c2c", "nd256"),
+    ((2, 256, 256, 256), True, "c2c", "nd256"),
+    ((1, 512, 512, 512), False, "c2c", "nd512"),
+    ((7, 640, 480), False, "c2c", "nd640"),
+    ((3, 640, 480), True, "c2c", "nd640"),
+    ((5, 640, 480), False, "real", "nd640"),
+    ((5, 640, 480), False, "half", "nd640"),
+    ((1, 640, 480), False, "c2c", "nd640"),
+    ((5, 64, 64, 64), False, "c2c", "+32_plane"),
+    ((37, 64, 64, 64), True, "c2c", "+32_plane"),
+    ((23, 64, 64, 64), False, "c2c", "+32_rows"),
+    ((3, 128, 128, 128), False, "c2c", "ndA128"),
+    ((2, 128, 128, 128), True, "c2c", "ndA128"),
+    ((1, 256, 256, 256), False, "c2c", "ndA256"),
+    ((2, 256, 256, 256), True, "c2c", "ndA256"),
+    ((1, 512, 512, 512), False, "c2c", "ndA512"),
+    ((7, 640, 480), False, "c2c", "ndA640"),
+    ((3, 640, 480), True, "c2c", "ndA640"),
+    ((5, 640, 480), False, "real", "ndA640"),
+    ((1, 640, 480), False, "c2c", "ndA640"),
 ]
 
 
 @pytest.mark.parametrize("shape,inverse,mode,prefer", CASES)
 def test_fused_matches_float64_and_per_axis_passes(shape, inverse, mode, prefer, monkeypatch):
     import torch
-    if prefer:
-        monkeypatch.setenv("B200FFT_FUSED_PREFER", prefer)
+    monkeypatch.setenv("B200FFT_FUSED_PREFER", prefer)
     comps = 2 if mode == "c2c" else 1
     g = torch.Generator(device="cuda").manual_seed(11)
     x = torch.randn(tuple(shape) + (comps,), generator=g, device="cuda")
@@ -67,8 +79,7 @@ def test_fused_matches_float64_and_per_axis_passes(shape, inverse, mode, prefer,
     rm = b200fft.REAL_HALF if mode == "half" else b200fft.REAL_FULL
     plan = b200fft.plan_fft("float32", "float32", x.shape, oshape, inverse=inverse, real_mode=rm)
     assert plan.describe().startswith("fused"), plan.describe()
-    if prefer:
-        assert prefer in plan.describe()
+    assert prefer in plan.describe(), plan.describe()
     assert plan.launches == 1
     out = torch.full(oshape, float("nan"), device="cuda")
     keep = x.clone()

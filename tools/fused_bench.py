@@ -45,7 +45,7 @@ def run(name, shape, mode, env, peak, steps=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chunks", default="8,16,32")
-    ap.add_argument("--prefer", default="plane,rows")
+    ap.add_argument("--prefer", default="+32_plane,+32_rows,t256_plane")
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     peak, _ = measured_peak()
@@ -53,7 +53,7 @@ def main():
         if a.only and a.only not in name:
             continue
         print(json.dumps(run(name, shape, mode, {"B200FFT_FUSED": "0"}, peak)), flush=True)
-        prefs = a.prefer.split(",") if name.startswith("3d") and ("64" in name or "128" in name) else [""]
+        prefs = a.prefer.split(",") if "64^3" in name else ["ndA", "nd" + name.split("x")[1].split("^")[0].split("_")[0]]
         for pref in prefs:
             for c in a.chunks.split(","):
                 env = {"B200FFT_FUSED": "1", "B200FFT_CHUNK_MB": c}
