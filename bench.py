@@ -131,6 +131,27 @@ def physical_gpu_index(local_index):
     return local_index
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so the pinned host buffers of
+    the e2e leg are first-touched on the GPU's own NUMA node (one process per GPU: otherwise every
+    rank's staging memory lands on one socket and the ranks share its memory / PCIe bandwidth)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 class CuFFT:
     """cuFFT through baseline/libcufft_shim.so (same call as the reference's cufft_benchmark.cu)."""
 
@@ -352,6 +373,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa(physical_gpu_index(local))
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -413,7 +435,8 @@ def main():
     e2e_ok = bool(torch.allclose(h_out[:4], out[:4].cpu(), rtol=0, atol=0))
     e2e = {"value": world * flops_c2c(shape) / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": plan.in_bytes, "d2h_bytes_per_step": plan.out_bytes,
-           "matches_device_path": e2e_ok, "api": "b200fft_exec_host (pinned host buffers, chunked 3-stream pipeline)"}
+           "matches_device_path": e2e_ok, "api": "b200fft_exec_host (pinned host buffers, chunked 3-stream pipeline)",
+           "host_cpus_bound": numa_cpus}
 
     # ---- N > 1: the single 512^3 transform, slab-decomposed over the ranks (exchange inside the timed region)
     slab = None

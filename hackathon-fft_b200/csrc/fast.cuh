@@ -102,6 +102,36 @@ struct GlobalDst {
     base[o * so + i * si + c] = v;
   }
 };
+// 128-bit variants for contiguous rows: lanes (2m, 2m+1) own butterflies n = 2m, 2m+1 whose inputs
+// x[n + j*NB] and outputs Y[.. + p + k*P] are ADJACENT in memory for every j / k. Each lane moves one
+// float4 (both butterflies' element) for half of the j's and the two lanes swap halves with one
+// __shfl_xor per element pair: every global access is a 16-byte LDG.128 / STG.128, a warp covers 512
+// contiguous bytes, and the exchange between the two butterflies stays inside the warp.
+struct GlobalSrcV4 {
+  static constexpr bool pairwise = true;
+  const float2* __restrict__ base;
+  long long so;
+  int valid_o;
+  __device__ __forceinline__ float4 load2(int o, int i_even) const {
+    if (o >= valid_o) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(reinterpret_cast<const float4*>(base + o * so + i_even));
+  }
+};
+struct GlobalDstV4 {
+  static constexpr bool pairwise = true;
+  float2* __restrict__ base;
+  long long so;
+  int valid_o;
+  __device__ __forceinline__ void store2(int o, int i_even, float4 v) const {
+    if (o >= valid_o) return;
+    *reinterpret_cast<float4*>(base + o * so + i_even) = v;
+  }
+};
+template <class T, class = void>
+struct is_pairwise : std::false_type {};
+template <class T>
+struct is_pairwise<T, std::enable_if_t<T::pairwise>> : std::true_type {};
+
 template <class Layout>
 struct SmemSrc {
   const float2* buf;
@@ -152,8 +182,25 @@ __device__ __forceinline__ void run_stage(const Src& src, const Dst& dst, const 
       const int p = (P == 1) ? 0 : n % P;
       const int g = (P == 1) ? n : n / P;
       float2 x[R];
+      if constexpr (is_pairwise<Src>::value) {
+        static_assert(CN == 1 && NB % 2 == 0 && R % 2 == 0 && NT % 2 == 0, "pairwise loads: even NB, R, NT");
+        const bool odd = (threadIdx.x & 1) != 0;
+        const unsigned mask = __activemask();
 #pragma unroll
-      for (int j = 0; j < R; ++j) x[j] = src.load(o, n + j * NB, c);
+        for (int jj = 0; jj < R / 2; ++jj) {
+          // this lane fetches row j = 2jj + odd of the pair (n & ~1, n | 1); the partner fetches the other
+          const float4 v = src.load2(o, (n & ~1) + (2 * jj + (odd ? 1 : 0)) * NB);
+          const float2 keep = odd ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+          float2 give = odd ? make_float2(v.x, v.y) : make_float2(v.z, v.w);
+          give.x = __shfl_xor_sync(mask, give.x, 1);
+          give.y = __shfl_xor_sync(mask, give.y, 1);
+          x[2 * jj] = odd ? give : keep;
+          x[2 * jj + 1] = odd ? keep : give;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) x[j] = src.load(o, n + j * NB, c);
+      }
       if constexpr (P > 1) {
 #pragma unroll
         for (int j = 1; j < R; ++j) x[j] = cmulf(x[j], tw_load<TWS>(tw, (j - 1) * P + p));
@@ -163,8 +210,24 @@ __device__ __forceinline__ void run_stage(const Src& src, const Dst& dst, const 
 #pragma unroll
         for (int k = 0; k < R; ++k) { x[k].x *= scale; x[k].y *= scale; }
       }
+      if constexpr (is_pairwise<Dst>::value) {
+        static_assert(CN == 1 && P % 2 == 0 && R % 2 == 0 && NT % 2 == 0, "pairwise stores: even P, R, NT");
+        const bool odd = (threadIdx.x & 1) != 0;
+        const unsigned mask = __activemask();
 #pragma unroll
-      for (int k = 0; k < R; ++k) dst.store(o, g * (P * R) + p + k * P, c, x[k]);
+        for (int kk = 0; kk < R / 2; ++kk) {
+          // outputs k of butterflies (p & ~1, p | 1) are adjacent: the even lane stores k = 2kk, the odd lane k = 2kk + 1
+          float2 give = odd ? x[2 * kk] : x[2 * kk + 1];
+          const float2 keep = odd ? x[2 * kk + 1] : x[2 * kk];
+          give.x = __shfl_xor_sync(mask, give.x, 1);
+          give.y = __shfl_xor_sync(mask, give.y, 1);
+          const float4 v = odd ? make_float4(give.x, give.y, keep.x, keep.y) : make_float4(keep.x, keep.y, give.x, give.y);
+          dst.store2(o, g * (P * R) + (p & ~1) + (2 * kk + (odd ? 1 : 0)) * P, v);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) dst.store(o, g * (P * R) + p + k * P, c, x[k]);
+      }
     }
   }
 }
@@ -232,7 +295,9 @@ struct RowsArgs {
 };
 
 // contiguous rows: tile = C consecutive transforms of length N, one tile per CTA
-template <int N, class RL, int C, int NT, bool INV, bool REAL>
+// VEC: 128-bit global accesses with an intra-warp shuffle exchange (GlobalSrcV4 / GlobalDstV4); needs complex
+// input, at least two stages and even N / R_0, R_last, P_last
+template <int N, class RL, int C, int NT, bool INV, bool REAL, bool VEC = false>
 __global__ void __launch_bounds__(NT) rows_kernel(const __grid_constant__ RowsArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
   constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
@@ -242,9 +307,15 @@ __global__ void __launch_bounds__(NT) rows_kernel(const __grid_constant__ RowsAr
   const int valid = (int)min((long long)C, a.nrows - row0);
   const void* in = REAL ? (const void*)(reinterpret_cast<const float*>(a.in) + row0 * N)
                         : (const void*)(reinterpret_cast<const float2*>(a.in) + row0 * N);
-  GlobalSrc<REAL> src{in, N, 1, valid, 1};
-  GlobalDst dst{a.out + row0 * N, N, 1, valid, 1};
-  run_axis<RL, N, C, 1, NT, INV, RowLayoutN<N>::template type>(src, dst, buf0, buf1, a.tw, a.scale, a.do_scale != 0);
+  if constexpr (VEC && !REAL) {
+    GlobalSrcV4 src{reinterpret_cast<const float2*>(a.in) + row0 * N, N, valid};
+    GlobalDstV4 dst{a.out + row0 * N, N, valid};
+    run_axis<RL, N, C, 1, NT, INV, RowLayoutN<N>::template type>(src, dst, buf0, buf1, a.tw, a.scale, a.do_scale != 0);
+  } else {
+    GlobalSrc<REAL> src{in, N, 1, valid, 1};
+    GlobalDst dst{a.out + row0 * N, N, 1, valid, 1};
+    run_axis<RL, N, C, 1, NT, INV, RowLayoutN<N>::template type>(src, dst, buf0, buf1, a.tw, a.scale, a.do_scale != 0);
+  }
 }
 template <int N, class RL, int C>
 constexpr size_t rows_smem_bytes() {

@@ -2,19 +2,28 @@
 // Order = preference (first variant whose super-stages can be grouped from the user's stage list).
 // Measured on B200 (tools/sweep.py, profiles/r1_sweep.md): one shared-memory exchange with two
 // large register codelets beats three smaller stages by 20-45 %.
+// reg_rows_v4 = the same kernel with 128-bit global loads/stores and a two-lane shuffle exchange
+// (fast.cuh: GlobalSrcV4): equal speed for 64/128/256 (0.1518 vs 0.1514 ms on 500000 x 128), so it is the
+// default there; with a radix-32 first stage the extra selects/shuffles cost 20 % (1024: 0.290 vs 0.237 ms,
+// 512^3: 1.22 vs 1.03 ms), so 512/1024 keep the 64-bit form (profiles/r1_vec128.md).
 #include "fast_registry.hpp"
 namespace b200fft {
 void register_rows_pow2() {
   reg_rows<8, 256, 256, true, 8>();
   reg_rows<16, 128, 128, true, 16>();
   reg_rows<32, 128, 128, true, 32>();
+  reg_rows_v4<64, 32, 256, true, 8, 8>();
   reg_rows<64, 32, 256, true, 8, 8>();
+  reg_rows_v4<128, 32, 256, true, 16, 8>();
   reg_rows<128, 32, 256, true, 16, 8>();
   reg_rows<128, 32, 256, true, 8, 16>();
+  reg_rows_v4<256, 16, 256, true, 16, 16>();
   reg_rows<256, 16, 256, true, 16, 16>();
   reg_rows<512, 8, 256, true, 32, 16>();
+  reg_rows_v4<512, 8, 256, true, 32, 16>();
   reg_rows<512, 8, 256, true, 8, 8, 8>();
   reg_rows<1024, 8, 256, true, 32, 32>();
+  reg_rows_v4<1024, 8, 256, true, 32, 32>();
   reg_rows<1024, 4, 256, true, 16, 16, 4>();
   reg_rows<2048, 4, 256, true, 32, 8, 8>();
   reg_rows<4096, 2, 256, true, 16, 16, 16>();

@@ -49,23 +49,24 @@ bool tensor_maps_available();
 
 // FULL variants instantiate forward/inverse x complex/real-input; tuning candidates only
 // forward complex (they are skipped for other requests).
-template <int N, class RL, int C, int NT, bool FULL>
+// VEC: complex-input instantiations use 128-bit global accesses + shuffle exchange (real input keeps 32-bit loads)
+template <int N, class RL, int C, int NT, bool FULL, bool VEC = false>
 struct RowsV {
   static void launch(bool inv, bool real, const RowsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
     if constexpr (FULL) {
       if (!inv && real) return (void)rows_kernel<N, RL, C, NT, false, true><<<grid, NT, smem, st>>>(a);
-      if (inv && !real) return (void)rows_kernel<N, RL, C, NT, true, false><<<grid, NT, smem, st>>>(a);
+      if (inv && !real) return (void)rows_kernel<N, RL, C, NT, true, false, VEC><<<grid, NT, smem, st>>>(a);
       if (inv && real) return (void)rows_kernel<N, RL, C, NT, true, true><<<grid, NT, smem, st>>>(a);
     }
-    rows_kernel<N, RL, C, NT, false, false><<<grid, NT, smem, st>>>(a);
+    rows_kernel<N, RL, C, NT, false, false, VEC><<<grid, NT, smem, st>>>(a);
   }
   static cudaError_t prepare(size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    cudaError_t e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, false>, attr, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, false, VEC>, attr, (int)smem);
     if constexpr (FULL) {
       if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, false, true>, attr, (int)smem);
-      if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, false>, attr, (int)smem);
+      if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, false, VEC>, attr, (int)smem);
       if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, true>, attr, (int)smem);
     }
     return e;
@@ -148,17 +149,18 @@ inline std::string radix_name(const std::vector<int>& r) {
   return s;
 }
 
-template <int N, int C, int NT, bool FULL, int... Rs>
-void reg_rows() {
+template <int N, int C, int NT, bool FULL, bool VEC, int... Rs>
+void reg_rows_impl() {
   using RL = Radices<Rs...>;
   static_assert(RL::product() == N, "radices must multiply to N");
   Variant v;
   v.kind = ROWS; v.n = N; v.radices = radix_vec<RL>(); v.tile = C; v.threads = NT;
   v.smem = rows_smem_bytes<N, RL, C>();
-  v.name = "rows" + std::to_string(N) + "_" + radix_name(v.radices) + "_c" + std::to_string(C) + "_t" + std::to_string(NT);
-  v.launch_rows = &RowsV<N, RL, C, NT, FULL>::launch;
+  v.name = std::string(VEC ? "rowsV" : "rows") + std::to_string(N) + "_" + radix_name(v.radices) + "_c" + std::to_string(C) +
+           "_t" + std::to_string(NT);
+  v.launch_rows = &RowsV<N, RL, C, NT, FULL, VEC>::launch;
   v.launch_cols = nullptr;
-  v.prepare = &RowsV<N, RL, C, NT, FULL>::prepare;
+  v.prepare = &RowsV<N, RL, C, NT, FULL, VEC>::prepare;
   if constexpr (FULL) {
     v.smem_r2c = rows_r2c_smem_bytes<N, RL, C>();
     v.smem_c2r = rows_c2r_smem_bytes<N, RL, C>();
@@ -169,6 +171,15 @@ void reg_rows() {
   }
   v.full = FULL;
   registry().push_back(v);
+}
+template <int N, int C, int NT, bool FULL, int... Rs>
+void reg_rows() {
+  reg_rows_impl<N, C, NT, FULL, false, Rs...>();
+}
+// 128-bit loads/stores + shuffle exchange for the complex-input instantiations ("rowsV..." variants)
+template <int N, int C, int NT, bool FULL, int... Rs>
+void reg_rows_v4() {
+  reg_rows_impl<N, C, NT, FULL, true, Rs...>();
 }
 template <int N, int CW, int NT, bool FULL, int... Rs>
 void reg_cols() {

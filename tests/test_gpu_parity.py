@@ -237,3 +237,25 @@ def test_full_size_properties(oracle, name, shape):
     torch.cuda.synchronize()
     assert torch.equal(back, out * 2)
     fwd.destroy(); inv.destroy()
+
+
+@pytest.mark.parametrize("shape", [(1000, 128), (37, 1024), (65, 64), (33, 512), (77, 256)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_vectorised_rows_variants(shape, inverse, monkeypatch):
+    """"rowsV" variants: 128-bit global loads/stores with the two-lane shuffle exchange (fast.cuh GlobalSrcV4)."""
+    import torch
+    monkeypatch.setenv("B200FFT_PREFER", "rowsV")
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(shape + (2,)).astype(np.float32)
+    plan = b200fft.plan_fft("float32", "float32", x.shape, x.shape, inverse=inverse)
+    assert "rowsV" in plan.describe(), plan.describe()
+    xt = torch.from_numpy(x).cuda()
+    out = torch.full_like(xt, float("nan"))
+    b200fft.fft(out, xt, plan=plan)
+    torch.cuda.synchronize()
+    want = (np.fft.ifft if inverse else np.fft.fft)(c2(x.astype(np.float64)), axis=1)
+    check_vs(out.cpu().numpy(), want, RTOL_L2_NP, RTOL_MAX_NP)
+    # in place, ragged last tile included (shape[0] is not a multiple of the rows per CTA)
+    b200fft.fft(xt, xt, plan=plan)
+    torch.cuda.synchronize()
+    assert torch.equal(xt, out)
