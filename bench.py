@@ -76,6 +76,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.marks = {}
         self._stop = threading.Event()
         self._thr = None
 
@@ -110,15 +111,20 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.001)
+
+    def mark(self, name):
+        self.marks[name] = len(self.samples)
 
     def stop(self):
         self._stop.set()
         if self._thr:
             self._thr.join()
         s = sorted(self.samples)
+        timed = self.marks.get("timed_end", len(self.samples)) - self.marks.get("timed_start", 0)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s), "samples_in_timed_region": timed,
+                "sampled": "NVML every ~1 ms during the timed steps and during a 0.3 s untimed continuation of the same step"}
 
 
 def physical_gpu_index(local_index):
@@ -399,12 +405,21 @@ def main():
     sampler = ClockSampler(physical_gpu_index(local)).start()
     launches0 = b200fft.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark("timed_start")
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark("timed_end")
     launches = b200fft.launch_count() - launches0
+    # the timed region lasts a few ms; keep the same step running (untimed) so the clock record has a
+    # meaningful median under load
+    t_end = time.perf_counter() + 0.3
+    while time.perf_counter() < t_end:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
     clocks = sampler.stop()
     if dist:
         dist.barrier()

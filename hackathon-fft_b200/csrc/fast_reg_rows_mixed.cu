@@ -6,6 +6,8 @@ void register_rows_mixed() {
   reg_rows<93, 32, 96, true, 31, 3>();
   reg_rows<93, 16, 48, false, 31, 3>();
   reg_rows<93, 64, 96, false, 31, 3>();
+  reg_rows<48, 64, 192, true, 16, 3>();     // 5-D (25,160,160,48), bench.mojo:121
+  reg_rows<160, 32, 320, true, 16, 10>();
   reg_rows<240, 16, 256, true, 16, 15>();
   reg_rows<320, 16, 256, true, 20, 16>();
   reg_rows<480, 8, 192, true, 24, 20>();
