@@ -325,7 +325,7 @@ def bench_slab(n, world, rank, torch, dist, steps=10, warmup=3):
     zl = n // world
     g = torch.Generator(device="cuda").manual_seed(77 + rank)
     x = torch.randn((zl, n, n, 2), generator=g, device="cuda")
-    for mode in ("p2p", "nccl"):
+    for mode in ("fused", "p2p", "nccl"):
         try:
             sl = SlabFFT3D((n, n, n), exchange=mode)
             for _ in range(warmup):

@@ -158,7 +158,12 @@ template <bool TWS>
 __device__ __forceinline__ float2 tw_load(const float2* tw, int idx) {
   if constexpr (TWS) {
     float2 v;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(tw + idx)));
+    // volatile + memory clobber: the table is written by other threads of the CTA before a barrier; the
+    // compiler must not hoist this load across that barrier (or out of a persistent kernel's tile loop)
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                 : "=f"(v.x), "=f"(v.y)
+                 : "r"((unsigned)__cvta_generic_to_shared(tw + idx))
+                 : "memory");
     return v;
   } else {
     return __ldg(tw + idx);

@@ -16,7 +16,7 @@ built and an sm_100 device is present.
 import ctypes
 import os
 
-__all__ = ["plan_fft", "fft", "Plan", "B200FFTError", "ordered_bases", "default_bases", "dry_run",
+__all__ = ["plan_fft", "fft", "Plan", "SlabPlan", "B200FFTError", "ordered_bases", "default_bases", "dry_run",
            "launch_count", "lib_path", "REAL_FULL", "REAL_HALF", "FLAG_FORCE_GENERIC", "FLAG_NO_CHUNKING", "FLAG_NO_FUSED"]
 
 MAX_RANK = 8
@@ -66,6 +66,12 @@ SYMBOLS = [
     ("b200fft_ipc_export", ctypes.c_int, [_vp, ctypes.c_char_p]),
     ("b200fft_ipc_open", ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     ("b200fft_ipc_close", ctypes.c_int, [_vp]),
+    ("b200fft_slab_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int]),
+    ("b200fft_slab_recv_bytes", ctypes.c_size_t, [_vp]),
+    ("b200fft_slab_exec", ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_vp), ctypes.c_int, _vp]),
+    ("b200fft_slab_describe", ctypes.c_size_t, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
+    ("b200fft_slab_destroy", ctypes.c_int, [_vp]),
     ("b200fft_plan_destroy", ctypes.c_int, [_vp]),
     ("b200fft_plan_workspace_bytes", ctypes.c_size_t, [_vp]),
     ("b200fft_plan_get_bases", ctypes.c_int, [_vp, ctypes.c_int, _u32p, ctypes.c_int]),
@@ -304,6 +310,41 @@ class Plan:
     def destroy(self):
         if self._h:
             lib().b200fft_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class SlabPlan:
+    """One rank's share of a slab-decomposed n^3 transform as a single fused kernel (b200fft_slab_*)."""
+
+    def __init__(self, n, ranks, rank, inverse=False, device=None):
+        h = ctypes.c_void_p()
+        _check(lib().b200fft_slab_create(ctypes.byref(h), n, ranks, rank, 1 if inverse else 0,
+                                         -1 if device is None else int(device)))
+        self._h = h
+        self.n, self.ranks, self.rank = n, ranks, rank
+
+    @property
+    def recv_bytes(self):
+        return int(lib().b200fft_slab_recv_bytes(self._h))
+
+    def exec(self, x, work, peer_recv, buffer, stream=None):
+        arr = (ctypes.c_void_p * len(peer_recv))(*[_ptr(p) for p in peer_recv])
+        _check(lib().b200fft_slab_exec(self._h, _ptr(x), _ptr(work), arr, buffer, _ptr(stream)))
+
+    def describe(self):
+        buf = ctypes.create_string_buffer(512)
+        lib().b200fft_slab_describe(self._h, buf, len(buf))
+        return buf.value.decode()
+
+    def destroy(self):
+        if self._h:
+            lib().b200fft_slab_destroy(self._h)
             self._h = None
 
     def __del__(self):

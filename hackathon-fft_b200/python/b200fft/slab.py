@@ -15,6 +15,11 @@ y = h*Y/G + y_local. Two exchange modes share the same kernels:
              all-reduce is the only collective (barrier before step 3).
   * "nccl" — the same scattering store targets a local pack buffer [G][Z/G][Y/G][X], followed
              by one all_to_all_single (the baseline; also what the gloo CPU tests exercise).
+  * "fused" — ONE persistent kernel per rank (b200fft_slab_exec, csrc/slab.cuh) runs all three steps:
+             the Y tiles store into the peers' slabs and bump per-x-block arrival counters on every rank
+             over NVLink, the Z tiles of an x-block start as soon as its counter is complete, so the
+             exchange overlaps the butterflies on both sides and there is no barrier at all. Cubic
+             volumes (64/128/256/512) only.
 
 SlabFFT3D owns the decomposition and exchange logic; an `engine` supplies the three local
 operations (alloc, fft2_scatter, fftz). The product engine is CUDA-only (no CPU fallback);
@@ -94,8 +99,8 @@ class SlabFFT3D:
         self.world = dist.get_world_size(group)
         self.dims = tuple(int(v) for v in dims)
         Z, Y, X = self.dims
-        if exchange not in ("p2p", "nccl"):
-            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if exchange not in ("p2p", "nccl", "fused"):
+            raise ValueError("exchange must be 'p2p', 'nccl' or 'fused'")
         if Z % self.world or Y % self.world:
             raise b200fft.B200FFTError(1, "slab decomposition needs Z and Y divisible by the number of ranks")
         self.exchange = exchange
@@ -103,6 +108,9 @@ class SlabFFT3D:
         if engine is None:
             if not torch.cuda.is_available():
                 raise b200fft.B200FFTError(5, "SlabFFT3D needs CUDA devices: there is no CPU path")
+            if exchange == "fused":
+                self._init_fused(inverse)
+                return
             engine = CudaSlabEngine(self.dims, self.world, inverse)
         self.engine = engine
         self.calls = 0
@@ -132,7 +140,44 @@ class SlabFFT3D:
             self.pack = engine.alloc((self.world, self.zl, self.yl, X, 2))
             self.recv = [engine.alloc((Z, self.yl, X, 2))]
 
+    def _init_fused(self, inverse):
+        Z, Y, X = self.dims
+        if not (Z == Y == X):
+            raise b200fft.B200FFTError(4, "the fused slab kernel covers cubic volumes only")
+        self.engine = None
+        self.calls = 0
+        self._opened = []
+        self.plan = b200fft.SlabPlan(Z, self.world, self.rank, inverse)
+        nfloat = self.plan.recv_bytes // 4
+        dev = torch.cuda.current_device()
+        self._bufs = [_DevBuf((nfloat,), dev) for _ in range(2)]
+        for b in self._bufs:
+            b.tensor.zero_()                      # arrival counters start at 0 (they only ever grow)
+        torch.cuda.synchronize()
+        self.recv = [b.tensor[:Z * self.yl * X * 2].view(Z, self.yl, X, 2) for b in self._bufs]
+        mine = [b200fft.ipc_export(b.ptr) for b in self._bufs]
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=self.group)   # also orders "zeroed" before any peer's first store
+        self.peer_targets = []
+        for k in range(2):
+            row = []
+            for r in range(self.world):
+                if r == self.rank:
+                    row.append(self._bufs[k].ptr)
+                else:
+                    p = b200fft.ipc_open(handles[r][k])
+                    self._opened.append(p)
+                    row.append(p)
+            self.peer_targets.append(row)
+        self.work = torch.empty((self.zl, Y, X, 2), device="cuda", dtype=torch.float32)
+        dist.barrier(group=self.group)
+
     def forward(self, x_local):
+        if self.exchange == "fused":
+            k = self.calls & 1
+            self.calls += 1
+            self.plan.exec(x_local, self.work, self.peer_targets[k], k, torch.cuda.current_stream().cuda_stream)
+            return self.recv[k]
         if self.exchange == "p2p":
             k = self.calls & 1
             self.calls += 1
@@ -151,5 +196,14 @@ class SlabFFT3D:
         for p in self._opened:
             b200fft.ipc_close(p)
         self._opened = []
+        if self.exchange == "fused" and getattr(self, "plan", None) is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)        # no peer may still be storing into buffers we free
+            self.recv = []
+            for b in self._bufs:
+                b.free()
+            self.plan.destroy()
+            self.plan = None
+            return
         if hasattr(self.engine, "close"):
             self.engine.close()

@@ -137,6 +137,22 @@ B200FFT_API int b200fft_ipc_export(void* d_ptr, unsigned char handle[B200FFT_IPC
 B200FFT_API int b200fft_ipc_open(const unsigned char handle[B200FFT_IPC_HANDLE_BYTES], void** d_ptr);
 B200FFT_API int b200fft_ipc_close(void* d_ptr);
 
+/* ---- Slab decomposition as ONE kernel per rank (slab.cuh): X rows, Y columns with the exchange fused into
+ * their stores, and the Z columns of the received slab, overlapped tile by tile; cross-GPU dependencies are
+ * per-x-block arrival counters that every rank bumps on every peer over NVLink (no barrier, no all-to-all).
+ * Cubic volumes n^3 with n in {64, 128, 256, 512}, n divisible by `ranks`. Every rank allocates TWO receive
+ * buffers of b200fft_slab_recv_bytes() with b200fft_malloc, ZEROES them, shares them over CUDA IPC and
+ * synchronises with its peers once before the first exec; calls alternate buffer = 0, 1, 0, ... and every rank
+ * must make the same sequence of calls. peer_recv[h] = rank h's buffer `buffer` (peer_recv[rank] = the local
+ * one); after the kernel the first n * (n/ranks) * n complex values of the local buffer hold out[z][y_local][x]. */
+typedef struct b200fft_slab b200fft_slab;
+B200FFT_API int b200fft_slab_create(b200fft_slab** slab, int64_t n, int ranks, int rank, int inverse, int device);
+B200FFT_API size_t b200fft_slab_recv_bytes(const b200fft_slab* slab);
+B200FFT_API int b200fft_slab_exec(b200fft_slab* slab, const void* d_in, void* d_work, void* const* peer_recv, int buffer,
+                                  void* cu_stream);
+B200FFT_API size_t b200fft_slab_describe(const b200fft_slab* slab, char* buf, size_t cap);
+B200FFT_API int b200fft_slab_destroy(b200fft_slab* slab);
+
 B200FFT_API int b200fft_plan_destroy(b200fft_plan* plan);
 
 /* ---- introspection (tests, harness) */

@@ -52,3 +52,36 @@ def test_exec_scatter_errors():
     with pytest.raises(b200fft.B200FFTError) as e:       # contiguous-axis pass has no scattering store
         rows.exec_scatter([x1, x1], 0, x1, torch.zeros_like(x1))
     assert e.value.status == 4
+
+
+@pytest.mark.parametrize("n", [64, 128, 256])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_fused_slab_kernel_single_rank(n, inverse):
+    """b200fft_slab_exec with one rank: all three phases, the x-block arrival counters and the alternating
+    receive buffers on one GPU (the multi-rank run over NVLink is tools/slab_check.py under torchrun)."""
+    import torch
+    plan = b200fft.SlabPlan(n, 1, 0, inverse)
+    assert "slab_fused" in plan.describe()
+    nfloat = plan.recv_bytes // 4
+    bufs = [torch.zeros(nfloat, device="cuda") for _ in range(2)]
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn((n, n, n, 2), generator=g, device="cuda")
+    keep = x.clone()
+    work = torch.empty_like(x)
+    xc = torch.view_as_complex(x.double().contiguous())
+    want = torch.fft.ifftn(xc) if inverse else torch.fft.fftn(xc)
+    for call in range(5):                      # counters keep growing across calls; buffers alternate
+        k = call & 1
+        plan.exec(x, work, [bufs[k]], k)
+        torch.cuda.synchronize()
+        got = torch.view_as_complex(bufs[k][:n * n * n * 2].view(n, n, n, 2).double().contiguous())
+        assert float((got - want).norm() / want.norm()) < 2e-6
+    assert torch.equal(x, keep)
+    plan.destroy()
+
+
+def test_fused_slab_rejects_unsupported():
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.SlabPlan(100, 1, 0)            # not a registered cubic size
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.SlabPlan(128, 3, 0)            # 128 planes cannot be split over 3 ranks

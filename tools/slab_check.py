@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """torchrun entry: slab-decomposed 3-D FFT across the node's GPUs, both exchange modes.
 
-    python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/slab_check.py [--n 512]
+    python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/slab_check.py [--size 512]
 
 1. correctness at 128^3: every rank's Y slab vs torch.fft.fftn of the gathered volume (rank 0 prints)
 2. timing at N^3 (default 512): K calls bracketed by barriers, CUDA events, max over ranks,
@@ -64,28 +64,40 @@ def bench(n, mode, rank, world, steps, warmup):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--size", dest="n", type=int, default=512)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--modes", default="nccl,p2p,fused")
+    ap.add_argument("--delays", default="", help="comma list of B200FFT_SLAB_DELAY values to time the fused mode with")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     res = {"world": world, "n": a.n}
-    for mode in ("nccl", "p2p"):
+    for mode in a.modes.split(","):
         try:
-            res["check128_" + mode] = check(128, mode, rank, world)
+            errs = check(128, mode, rank, world)
+            res["check128_" + mode] = {"max_rel_l2": max(e for e, _ in errs), "repeat_identical": all(s for _, s in errs)}
             res["ms_%d_%s" % (a.n, mode)] = bench(a.n, mode, rank, world, a.steps, a.warmup)
-        except Exception as e:  # report, keep going with the other mode
+        except Exception as e:  # report, keep going with the other modes
             res["error_" + mode] = "%s: %s" % (type(e).__name__, e)
+    for d in [v for v in a.delays.split(",") if v]:
+        os.environ["B200FFT_SLAB_DELAY"] = d
+        try:
+            res["ms_%d_fused_delay%s" % (a.n, d)] = bench(a.n, "fused", rank, world, a.steps, a.warmup)
+        except Exception as e:
+            res["error_fused_delay" + d] = "%s: %s" % (type(e).__name__, e)
     if rank == 0:
         import math
         pts = a.n ** 3
-        for mode in ("nccl", "p2p"):
-            k = "ms_%d_%s" % (a.n, mode)
-            if k in res:
-                res["gflops_" + mode] = 5 * pts * math.log2(pts) / res[k] / 1e6
-        print(json.dumps(res))
+        for k in [k for k in res if k.startswith("ms_")]:
+            res["gflops" + k[2:]] = 5 * pts * math.log2(pts) / res[k] / 1e6
+        line = json.dumps(res)
+        print(line)
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "slab_check_w%d.jsonl" % world), "a") as f:
+            f.write(line + "\n")
     dist.barrier()
     dist.destroy_process_group()
 
