@@ -65,7 +65,10 @@ AxisView view_of(const Problem& p, int axis) {
 std::unique_ptr<Pass> make_pass(b200fft_plan* plan, int axis, const AxisView& view, const IoSpec& src, HalfMode half) {
   const Problem& p = plan->prob;
   std::unique_ptr<Pass> pass;
-  if (!(p.desc.flags & B200FFT_FLAG_FORCE_GENERIC)) pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+  if (!(p.desc.flags & B200FFT_FLAG_FORCE_GENERIC)) {
+    pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+    if (!pass) pass = make_split_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+  }
   if (!pass) pass = make_generic_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
   return pass;
 }

@@ -578,4 +578,81 @@ constexpr size_t cols_smem_bytes() {
          (RL::count > 2 ? 2 : 1);
 }
 
+// ---- long axes as two passes ("four-step") ---------------------------------------------------------
+// An axis of length N = N1*N2 that is too long for one tile is transformed as
+//   A: N1-point transforms over n1 (element stride N2*inner), output (k1, n2) multiplied by W_N^{k1*n2}
+//   B: N2-point transforms over n2 (element stride inner) for every k1, output k2 stored at index
+//      k1 + N1*k2 of the axis (natural order, so no transpose pass)
+// Both are ordinary tile passes: A is a strided-axis pass with a twiddling store, B is a strided-axis
+// pass (or, for a contiguous axis, a row pass) whose destination uses a different base and stride.
+struct SplitArgs {
+  const float2* in;
+  float2* out;
+  const float2* tw;    // stage twiddles of this pass's variant
+  const float2* twN;   // W_N^n, n in [0, N): pass A only
+  long long inner;     // element stride of the ORIGINAL axis (1 = contiguous)
+  long long nrows;     // rows pass B: outer * N1 rows of N2 points
+  int tiles_per_outer; // cols passes: tiles per outer slab of THIS pass's view
+  int n1, n2;
+  float scale;
+  int do_scale;
+};
+
+struct SplitTwDst {
+  float2* __restrict__ base;
+  long long si;
+  int valid_c;
+  const float2* __restrict__ twN;
+  long long c0, inner;
+  __device__ __forceinline__ void store(int, int i, int c, float2 v) const {
+    if (c >= valid_c) return;
+    const int n2 = (int)((c0 + c) / inner);  // k1 * n2 < N1 * N2 = N: no reduction needed
+    base[i * si + c] = cmulf(v, __ldg(&twN[i * n2]));
+  }
+};
+
+// pass A: view (outer, N1 = N, inner' = n2 * inner)
+template <int N, class RL, int CW, int NT, bool INV>
+__global__ void __launch_bounds__(NT) cols_split_a_kernel(const __grid_constant__ SplitArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
+  const long long vinner = (long long)a.n2 * a.inner;
+  const long long o = blockIdx.x / a.tiles_per_outer;
+  const long long c0 = (long long)(blockIdx.x - o * a.tiles_per_outer) * CW;
+  const long long base = o * N * vinner + c0;
+  const int valid_c = (int)min((long long)CW, vinner - c0);
+  GlobalSrc<false> src{a.in + base, 0, vinner, 1, valid_c};
+  SplitTwDst dst{a.out + base, vinner, valid_c, a.twN, c0, a.inner};
+  run_axis<RL, N, 1, CW, NT, INV, DenseLayoutN<N, CW>::template type>(src, dst, smem_f2, smem_f2 + BUF, a.tw, 1.f, false);
+}
+
+// pass B on a strided axis: view (outer * n1, N2 = N, inner); row k2 of slab (o, k1) goes to axis index k1 + n1*k2
+template <int N, class RL, int CW, int NT, bool INV>
+__global__ void __launch_bounds__(NT) cols_split_b_kernel(const __grid_constant__ SplitArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
+  const long long ov = blockIdx.x / a.tiles_per_outer;  // o * n1 + k1
+  const long long c0 = (long long)(blockIdx.x - ov * a.tiles_per_outer) * CW;
+  const long long o = ov / a.n1, k1 = ov - o * a.n1;
+  const int valid_c = (int)min((long long)CW, a.inner - c0);
+  GlobalSrc<false> src{a.in + ov * N * a.inner + c0, 0, a.inner, 1, valid_c};
+  GlobalDst dst{a.out + (o * N * a.n1 + k1) * a.inner + c0, 0, (long long)a.n1 * a.inner, 1, valid_c};
+  run_axis<RL, N, 1, CW, NT, INV, DenseLayoutN<N, CW>::template type>(src, dst, smem_f2, smem_f2 + BUF, a.tw, a.scale,
+                                                                      a.do_scale != 0);
+}
+
+// pass B on a contiguous axis (inner == 1): C consecutive rows k1 of one transform, N2 = N points each
+template <int N, class RL, int C, int NT, bool INV>
+__global__ void __launch_bounds__(NT) rows_split_b_kernel(const __grid_constant__ SplitArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
+  const long long row0 = (long long)blockIdx.x * C;  // rows never straddle transforms: C divides n1
+  const int valid = (int)min((long long)C, a.nrows - row0);
+  const long long t = row0 / a.n1, k1 = row0 - t * a.n1;
+  GlobalSrc<false> src{a.in + row0 * N, N, 1, valid, 1};
+  GlobalDst dst{a.out + t * N * a.n1 + k1, 1, a.n1, valid, 1};  // element (row o, k2) -> k1 + o + n1 * k2
+  run_axis<RL, N, C, 1, NT, INV, RowLayoutN<N>::template type>(src, dst, smem_f2, smem_f2 + BUF, a.tw, a.scale,
+                                                               a.do_scale != 0);
+}
+
 }  // namespace b200fft

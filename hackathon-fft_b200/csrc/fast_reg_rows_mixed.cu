@@ -15,6 +15,10 @@ void register_rows_mixed() {
   reg_rows<480, 16, 384, false, 24, 20>();
   reg_rows<480, 8, 256, false, 30, 16>();
   reg_rows<640, 8, 256, true, 32, 20>();
+  // contiguous axes of the reference's 1080p / 4K / 8K shapes (bench.mojo:112-115)
+  reg_rows<1080, 4, 144, true, 36, 30>();
+  reg_rows<2160, 2, 288, true, 16, 15, 9>();
+  reg_rows<4320, 1, 288, true, 16, 18, 15>();
   reg_rows<640, 4, 256, true, 10, 8, 8>();
 }
 }  // namespace b200fft

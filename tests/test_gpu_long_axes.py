@@ -1,0 +1,63 @@
+"""Axes too long for one tile run as two passes ("four-step": N = N1*N2, twiddle fused into pass A's store,
+natural-order store in pass B; csrc/split_registry.cu), plus the row variants for 1080 / 2160 / 4320: the
+remaining shapes the reference publishes (fft/bench.mojo:107-122), against torch float64."""
+import numpy as np
+import pytest
+
+import b200fft
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(shape, inverse=False, bases=None):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(tuple(shape) + (2,), generator=g, device="cuda")
+    out = torch.full_like(x, float("nan"))
+    plan = b200fft.plan_fft("float32", "float32", x.shape, x.shape, inverse=inverse, bases=bases)
+    keep = x.clone()
+    b200fft.fft(out, x, plan=plan)
+    torch.cuda.synchronize()
+    assert torch.equal(x, keep)
+    xc = torch.view_as_complex(x.double().contiguous())
+    axes = tuple(range(1, xc.dim()))
+    want = torch.fft.ifftn(xc, dim=axes) if inverse else torch.fft.fftn(xc, dim=axes)
+    got = torch.view_as_complex(out.double().contiguous())
+    rel = float((got - want).norm() / want.norm())
+    mx = float((got - want).abs().max() / want.abs().max())
+    desc = plan.describe()
+    plan.destroy()
+    return rel, mx, desc
+
+
+@pytest.mark.parametrize("shape,inverse", [((3, 16384), False), ((2, 16384), True), ((100, 16384), False)])
+def test_contiguous_long_axis(shape, inverse):
+    rel, mx, desc = _run(shape, inverse)
+    assert "split n=16384 = 128 x 128" in desc and "splitB_rows128" in desc, desc
+    assert rel < 2e-6 and mx < 1e-5, (rel, mx)
+
+
+@pytest.mark.parametrize("shape,inverse", [((2, 1920, 1080), False), ((1, 1920, 1080), True),
+                                           ((1, 3840, 2160), False), ((1, 7680, 4320), False)])
+def test_published_2d_shapes(shape, inverse):
+    rel, mx, desc = _run(shape, inverse)
+    lines = desc.strip().split("\n")
+    assert lines[0].startswith("axis 1: rows%d_" % shape[2]), desc          # contiguous axis: one row kernel
+    assert "split n=%d = " % shape[1] in lines[1], desc                     # strided axis: two passes
+    assert "generic" not in desc
+    assert rel < 2e-6 and mx < 1e-5, (rel, mx)
+
+
+def test_published_4d_5d_shapes():
+    rel, mx, desc = _run((1, 64, 64, 64, 64))
+    assert "generic" not in desc and rel < 2e-6 and mx < 1e-5, (rel, mx, desc)
+    rel, mx, desc = _run((1, 25, 160, 160, 48))
+    assert "generic" not in desc and rel < 2e-6 and mx < 1e-5, (rel, mx, desc)
+
+
+def test_split_respects_user_bases():
+    """Bases that cannot be grouped into any (N1, N2) kernel pair fall back to the generic kernel."""
+    rel, mx, desc = _run((2, 1920, 64), bases=[[64, 30], [64]])      # 64*30: no such pair registered
+    assert "split" not in desc.split("\n")[1] and rel < 2e-6, desc
+    rel, mx, desc = _run((2, 1920, 64), bases=[[16, 8, 15], [8, 8]])  # groupable into (16,8) x (15)
+    assert "split n=1920 = 128 x 15" in desc and rel < 2e-6, desc
