@@ -283,6 +283,13 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
     }
   }
   if (cands.empty()) return nullptr;
+  if (kind == COLS && half == HALF_NONE) {
+    // a tile wider than the axis's inner extent would leave lanes idle: prefer variants that fit
+    std::vector<const Variant*> fit;
+    for (const Variant* v : cands)
+      if (v->tile <= view.inner) fit.push_back(v);
+    if (!fit.empty()) cands.swap(fit);
+  }
   if (const char* pref = getenv("B200FFT_PREFER")) {
     std::string s(pref);
     size_t pos = 0;
