@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -391,7 +392,9 @@ int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in) {
     // chunks of ~24 MiB (fill / drain of the 3-stage pipeline costs one chunk each way), at least 4 and
     // at most 64 of them, at least 1 batch item each
     const size_t per = std::max(in_stride, out_stride);
-    int64_t nchunks = (int64_t)(((size_t)p.batch * per + ((size_t)24 << 20) - 1) / ((size_t)24 << 20));
+    size_t chunk_mb = 24;  // B200FFT_HOST_CHUNK_MB: tuning knob (profiles/r1_e2e.md)
+    if (const char* e = getenv("B200FFT_HOST_CHUNK_MB")) chunk_mb = (size_t)std::max(1, atoi(e));
+    int64_t nchunks = (int64_t)(((size_t)p.batch * per + (chunk_mb << 20) - 1) / (chunk_mb << 20));
     nchunks = std::min<int64_t>(64, std::max<int64_t>(4, nchunks));
     int64_t chunk = std::max<int64_t>(1, (p.batch + nchunks - 1) / nchunks);
     if (plan->chunk_batches > 0) chunk = ((chunk + plan->chunk_batches - 1) / plan->chunk_batches) * plan->chunk_batches;
