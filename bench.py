@@ -348,6 +348,8 @@ def bench_slab(n, world, rank, torch, dist, steps=10, warmup=3):
             dist.all_reduce(e)
             res[mode] = {"ms": ms, "gflops": 5.0 * n ** 3 * math.log2(n ** 3) / ms / 1e6,
                          "parseval_rel_err": abs(float(e[0] / (e[1] * n ** 3)) - 1.0)}
+            if mode == "fused":
+                res[mode]["peer_wait_timeouts"] = sl.timeouts()
             sl.close()
             del out
         except Exception as ex:  # report, keep the bench line

@@ -105,7 +105,8 @@ int b200fft_slab_create(b200fft_slab** out, int64_t n, int ranks, int rank, int 
   s->zl = s->yl = (int)(n / ranks);
   s->nb = (int)(n / s->cw);
   s->slab_bytes = (size_t)n * s->yl * n * sizeof(float2);
-  s->recv_bytes = s->slab_bytes + (((size_t)s->nb * sizeof(unsigned) + 255) / 256) * 256;
+  // [slab][nb arrival counters][1 time-out counter], rounded up to 256 B
+  s->recv_bytes = s->slab_bytes + (((size_t)(s->nb + 1) * sizeof(unsigned) + 255) / 256) * 256;
 
   int rc = upload(build_twiddles(s->radices, s->inverse), &s->twx);
   if (!rc) rc = upload(build_twiddles(s->radices, s->inverse), &s->twy);
@@ -160,6 +161,8 @@ int b200fft_slab_create(b200fft_slab** out, int64_t n, int ranks, int rank, int 
 }
 
 size_t b200fft_slab_recv_bytes(const b200fft_slab* s) { return s ? s->recv_bytes : 0; }
+
+size_t b200fft_slab_timeout_offset(const b200fft_slab* s) { return s ? s->slab_bytes + (size_t)s->nb * sizeof(unsigned) : 0; }
 
 size_t b200fft_slab_describe(const b200fft_slab* s, char* buf, size_t cap) {
   if (!s) return 0;

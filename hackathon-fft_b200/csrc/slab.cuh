@@ -148,8 +148,18 @@ __global__ void __launch_bounds__(NT, 2) slab_fused_kernel(const __grid_constant
       __syncthreads();
       if (!s_ready) {
         flush_signal();
-        if (threadIdx.x == 0)
-          while ((int)(ld_acquire_sys(cnt) - a.want) < 0) __nanosleep(100);
+        if (threadIdx.x == 0) {
+          // bounded (~2 s): a peer that never arrives (crashed rank, mismatched call sequence) must not hang
+          // the GPU; the time-out is recorded in the word after the counters and the results are then invalid
+          unsigned spins = 0;
+          while ((int)(ld_acquire_sys(cnt) - a.want) < 0) {
+            __nanosleep(100);
+            if (++spins > 20000000u) {
+              atomicAdd(a.peer_ctr[a.rank] + a.nb, 1u);
+              break;
+            }
+          }
+        }
         __syncthreads();
       }
       const long long inner = (long long)a.yl * NX;

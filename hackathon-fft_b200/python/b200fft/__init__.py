@@ -69,6 +69,7 @@ SYMBOLS = [
     ("b200fft_slab_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int]),
     ("b200fft_slab_recv_bytes", ctypes.c_size_t, [_vp]),
+    ("b200fft_slab_timeout_offset", ctypes.c_size_t, [_vp]),
     ("b200fft_slab_exec", ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_vp), ctypes.c_int, _vp]),
     ("b200fft_slab_describe", ctypes.c_size_t, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
     ("b200fft_slab_destroy", ctypes.c_int, [_vp]),
@@ -332,6 +333,10 @@ class SlabPlan:
     @property
     def recv_bytes(self):
         return int(lib().b200fft_slab_recv_bytes(self._h))
+
+    @property
+    def timeout_offset(self):
+        return int(lib().b200fft_slab_timeout_offset(self._h))
 
     def exec(self, x, work, peer_recv, buffer, stream=None):
         arr = (ctypes.c_void_p * len(peer_recv))(*[_ptr(p) for p in peer_recv])

@@ -172,6 +172,14 @@ class SlabFFT3D:
         self.work = torch.empty((self.zl, Y, X, 2), device="cuda", dtype=torch.float32)
         dist.barrier(group=self.group)
 
+    def timeouts(self):
+        """fused mode: Z tiles that gave up waiting for a peer (0 unless a rank died or skipped a call). Synchronises."""
+        if self.exchange != "fused":
+            return 0
+        torch.cuda.synchronize()
+        w = self.plan.timeout_offset // 4
+        return int(sum(int(b.tensor[w:w + 1].view(torch.int32).item()) for b in self._bufs))
+
     def forward(self, x_local):
         if self.exchange == "fused":
             k = self.calls & 1

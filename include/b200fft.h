@@ -148,6 +148,9 @@ B200FFT_API int b200fft_ipc_close(void* d_ptr);
 typedef struct b200fft_slab b200fft_slab;
 B200FFT_API int b200fft_slab_create(b200fft_slab** slab, int64_t n, int ranks, int rank, int inverse, int device);
 B200FFT_API size_t b200fft_slab_recv_bytes(const b200fft_slab* slab);
+/* byte offset, inside a receive buffer, of a uint32 that counts Z tiles whose wait for the peers timed out (~2 s);
+ * non-zero after a synchronise means the result of that call is invalid (a rank died or skipped a call) */
+B200FFT_API size_t b200fft_slab_timeout_offset(const b200fft_slab* slab);
 B200FFT_API int b200fft_slab_exec(b200fft_slab* slab, const void* d_in, void* d_work, void* const* peer_recv, int buffer,
                                   void* cu_stream);
 B200FFT_API size_t b200fft_slab_describe(const b200fft_slab* slab, char* buf, size_t cap);
