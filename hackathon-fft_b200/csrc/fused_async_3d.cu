@@ -8,10 +8,11 @@ static void reg3d_async() {
   using R16x8 = Radices<16, 8>;
   using R16x16 = Radices<16, 16>;
   using R32x16 = Radices<32, 16>;
+  reg_fused_async<256, 2, APlane<64, 64, R8x8, R8x8, INV>, ACols<64, R8x8, 64, INV>>({64, 64, 64}, 0, "z64", 1);
   reg_fused_async<256, 2, APlane<64, 64, R8x8, R8x8, INV>, ACols<64, R8x8, 32, INV>>({64, 64, 64}, 0);
   reg_fused_async<256, 2, ARows<64, R8x8, 32, INV, false>, ACols<64, R8x8, 32, INV>, ACols<64, R8x8, 32, INV>>({64, 64, 64}, 0);
   reg_fused_async<256, 2, ARows<128, R16x8, 32, INV, false>, ACols<128, R16x8, 32, INV>, ACols<128, R16x8, 32, INV>>(
-      {128, 128, 128}, 0);
+      {128, 128, 128}, 0, "", 4);
   reg_fused_async<256, 2, ARows<256, R16x16, 16, INV, false>, ACols<256, R16x16, 16, INV>, ACols<256, R16x16, 16, INV>>(
       {256, 256, 256}, 0);
   reg_fused_async<256, 2, ARows<512, R32x16, 8, INV, false>, ACols<512, R32x16, 8, INV>, ACols<512, R32x16, 8, INV>>(

@@ -4,9 +4,9 @@
 // A fused variant replaces ALL per-axis passes of a plan (api.cu: build_passes tries it first). It is
 // used when every axis is transformed, the data is fp32, and the user's stage lists can be grouped
 // into the variant's super-stages (same rule as the per-axis variants, fast_registry.cu).
-//   B200FFT_FUSED=1        use fused variants (default off, see make_fused_pass; plan flag
-//                          B200FFT_FLAG_NO_FUSED always wins)
-//   B200FFT_CHUNK_MB=<n>   pipeline chunk size (default 16): how much phase-0 output is produced per
+//   B200FFT_FUSED=1 / 0    use every matching fused variant / none; unset = only the variants measured to win
+//                          (see make_fused_pass; plan flag B200FFT_FLAG_NO_FUSED always wins)
+//   B200FFT_CHUNK_MB=<n>   pipeline chunk size (default 8): how much phase-0 output is produced per
 //                          round; ~2-3 chunks are live in L2 at any time
 //   B200FFT_FUSED_PREFER=substr   prefer variants whose name contains substr (tuning aid)
 #include <cuda_runtime.h>
@@ -136,11 +136,11 @@ struct FusedPass : Pass {
 std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
   register_all_fused();
   const Problem& p = plan.prob;
-  // Measured on B200 (profiles/r1_fused_v1.md): this first version keeps HBM traffic at one read + one
-  // write but is latency-bound per tile and does not beat the per-axis kernels yet, so it is opt-in.
-  bool enabled = false;
-  if (const char* e = getenv("B200FFT_FUSED")) enabled = atoi(e) != 0;
-  if (!enabled) return nullptr;
+  // B200FFT_FUSED=1: any matching fused variant; =0: none; unset: only the variants measured to beat the
+  // per-axis kernels (default_min_batch > 0: 64^3 at every batch, 128^3 from batch 4; profiles/r1_fused_v1.md)
+  int mode_env = -1;
+  if (const char* e = getenv("B200FFT_FUSED")) mode_env = atoi(e) != 0;
+  if (mode_env == 0) return nullptr;
   if (p.desc.flags & (B200FFT_FLAG_FORCE_GENERIC | B200FFT_FLAG_NO_FUSED)) return nullptr;
   if (p.desc.out_dtype != B200FFT_F32 || p.desc.in_dtype != B200FFT_F32) return nullptr;
   if (p.rank < 2 || p.rank > 3) return nullptr;
@@ -162,6 +162,7 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
   for (int round = prefer ? 0 : 1; round < 2 && !pick; ++round) {  // round 0: preferred names only
     for (const FusedVariant& v : fused_registry()) {
       if (round == 0 && v.name.find(prefer) == std::string::npos) continue;
+      if (mode_env < 0 && (v.default_min_batch <= 0 || p.batch < v.default_min_batch)) continue;
       if ((int)v.dims.size() != p.rank || v.inverse != (p.desc.inverse != 0) || v.mode != mode) continue;
       bool ok = true;
       for (int a = 0; a < p.rank; ++a) ok = ok && v.dims[a] == dims[a];
@@ -235,7 +236,7 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
   const bool inv = p.desc.inverse != 0;
   double total_scale = 1.0;
   for (int a = 0; a < p.rank; ++a) total_scale *= (double)dims[a];
-  long long chunk_mb = 16;
+  long long chunk_mb = 8;  // 64^3 x100: 8 -> 0.1472, 12 -> 0.1464, 16 -> 0.1483 ms; 128^3 x10: 8 -> 0.1457, 12 -> 0.1474
   if (const char* e = getenv("B200FFT_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));
   std::string desc;
   for (int q = 0; q < v.nphases; ++q) {

@@ -30,6 +30,7 @@ struct FusedVariant {
   size_t smem = 0;
   void (*launch)(const NdArgs&, unsigned, size_t, cudaStream_t) = nullptr;
   // v2 (fused2.cuh): producer warp + bulk-async staging; threads = consumers + 32
+  int default_min_batch = 0;  // > 0: used without B200FFT_FUSED=1 when the batch is at least this (measured wins only)
   bool async = false;
   void (*launch_async)(const NdArgs&, const CUtensorMap&, const CUtensorMap&, unsigned, size_t, cudaStream_t) = nullptr;
   const void* func = nullptr;
@@ -99,7 +100,7 @@ void reg_fused(std::vector<int> dims, int mode, const char* tag = "") {
 
 // v2 variants: <consumer threads, min CTAs per SM, async phase types...>(dims, mode)
 template <int NT, int MINB, class P0, class P1, class P2 = ANone>
-void reg_fused_async(std::vector<int> dims, int mode, const char* tag = "") {
+void reg_fused_async(std::vector<int> dims, int mode, const char* tag = "", int default_min_batch = 0) {
   FusedVariant v;
   v.dims = dims;
   v.inverse = P1::inverse;
@@ -111,6 +112,7 @@ void reg_fused_async(std::vector<int> dims, int mode, const char* tag = "") {
   v.threads = NT + 32;
   v.smem = nd_async_smem<P0, P1, P2>();
   v.async = true;
+  v.default_min_batch = default_min_batch;
   v.launch_async = &FusedAsyncV<NT, MINB, P0, P1, P2>::launch;
   v.func = (const void*)nd_async_kernel<NT, MINB, P0, P1, P2>;
   std::string name = "ndA";
