@@ -121,8 +121,11 @@ class ClockSampler:
         if self._thr:
             self._thr.join()
         s = sorted(self.samples)
-        timed = self.marks.get("timed_end", len(self.samples)) - self.marks.get("timed_start", 0)
-        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+        t0, t1 = self.marks.get("timed_start", 0), self.marks.get("timed_end", len(self.samples))
+        timed = t1 - t0
+        ts = sorted(self.samples[t0:t1])
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_mhz_timed_region": (ts[len(ts) // 2] if ts else None),
+                "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(s), "samples_in_timed_region": timed,
                 "sampled": "NVML every ~1 ms during the timed steps and during a 0.3 s untimed continuation of the same step"}
 
