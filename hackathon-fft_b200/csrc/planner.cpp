@@ -176,7 +176,7 @@ int validate(const b200fft_desc* d, Problem* out) {
   if (p.half) {
     const AxisSpec& last = p.axes[d->rank - 1];
     if (!last.transformed) return fail(B200FFT_ERR_INVALID_ARG, "REAL_HALF needs the last axis transformed");
-    if (last.n % 2) return fail(B200FFT_ERR_UNSUPPORTED, "REAL_HALF needs an even last axis (got %lld)", (long long)last.n);
+    // odd last axes are served by the generic kernel's Hermitian load / store (the fused R2C/C2R kernels need n = 2H)
     if (d->in_dtype == B200FFT_U8) return fail(B200FFT_ERR_UNSUPPORTED, "REAL_HALF takes floating-point input");
     const int64_t lead = prod / last.n, hc = last.n / 2 + 1;
     if (!d->inverse) {

@@ -58,7 +58,7 @@ enum {
      stage 0 of the last axis and the output is the FULL N-bin complex spectrum. */
   B200FFT_REAL_FULL = 0,
   /* cuFFT-style half spectrum (new functionality, north-star piece 3):
-     forward: real (.., n_last) -> complex (.., n_last/2+1);
+     forward: real (.., n_last) -> complex (.., n_last/2+1)   (n_last even or odd);
      inverse: complex (.., n_last/2+1) -> real (.., n_last), scaled 1/prod(dims). */
   B200FFT_REAL_HALF = 1
 };

@@ -49,7 +49,8 @@ def c2r(X, n_last, generic=False, dtype=np.float32):
 
 
 SHAPES = [(8, 128), (5, 64), (3, 16), (7, 480), (4, 1024), (3, 640, 480), (2, 64, 64, 64), (2, 20, 12), (3, 6, 10, 8),
-          (2, 256), (3, 2), (2, 640), (2, 512), (1, 128, 128, 128)]
+          (2, 256), (3, 2), (2, 640), (2, 512), (1, 128, 128, 128),
+          (5, 93), (2, 7), (3, 15, 9), (2, 6, 4, 21)]  # odd last axis: generic Hermitian kernel
 
 
 @pytest.mark.parametrize("generic", [False, True])
@@ -128,6 +129,9 @@ def test_f64_and_errors():
     got, _ = r2c(x, dtype=np.float64)
     want = np.fft.rfft(x[..., 0], axis=1)
     assert np.linalg.norm(c2(got) - want) <= 1e-13 * np.linalg.norm(want)
-    with pytest.raises(b200fft.B200FFTError) as e:     # odd last axis: documented as unsupported
-        b200fft.plan_fft("float32", "float32", (2, 93, 1), (2, 47, 2), real_mode=b200fft.REAL_HALF)
+    with pytest.raises(b200fft.B200FFTError) as e:     # uint8 input is not accepted in half-spectrum mode
+        b200fft.plan_fft("uint8", "float32", (2, 32, 1), (2, 17, 2), real_mode=b200fft.REAL_HALF)
     assert e.value.status == 4
+    with pytest.raises(b200fft.B200FFTError) as e:     # wrong number of bins for the real length
+        b200fft.plan_fft("float32", "float32", (2, 93, 1), (2, 46, 2), real_mode=b200fft.REAL_HALF)
+    assert e.value.status == 2
