@@ -197,6 +197,7 @@ def test_errors_are_reported_not_thrown():
 FULL = [
     ("1d_500000x128", (500000, 128)), ("1d_100000x1024", (100000, 1024)), ("1d_500000x93", (500000, 93)),
     ("2d_100x640x480", (100, 640, 480)), ("3d_100x64^3", (100, 64, 64, 64)), ("3d_10x128^3", (10, 128, 128, 128)),
+    ("3d_1x512^3", (1, 512, 512, 512)),
 ]
 
 
@@ -224,7 +225,8 @@ def test_full_size_properties(oracle, name, shape):
         xb = x[b:b + 1].cpu().numpy()
         want = np.fft.fftn(c2(xb), axes=tuple(range(1, len(shape))))
         check_vs(out[b:b + 1].cpu().numpy(), want, RTOL_L2_NP, RTOL_MAX_NP)
-        check_vs(out[b:b + 1].cpu().numpy(), c2(oracle.ref_fft(xb)), RTOL_L2_ORACLE, RTOL_MAX_ORACLE)
+        if n <= 2 ** 21:   # the oracle's radix-2 CPU path on 512^3 alone would take a minute
+            check_vs(out[b:b + 1].cpu().numpy(), c2(oracle.ref_fft(xb)), RTOL_L2_ORACLE, RTOL_MAX_ORACLE)
     # round trip
     back = torch.full_like(x, float("nan"))
     b200fft.fft(back, out, plan=inv)
