@@ -69,6 +69,7 @@ std::unique_ptr<Pass> make_pass(b200fft_plan* plan, int axis, const AxisView& vi
   if (!(p.desc.flags & B200FFT_FLAG_FORCE_GENERIC)) {
     pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
     if (!pass) pass = make_split_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+    if (!pass) pass = make_rt_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
   }
   if (!pass) pass = make_generic_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
   return pass;

@@ -94,6 +94,9 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
 // long axes as two passes (split_registry.cu); nullptr when no (N1, N2) pair of kernels covers the length
 std::unique_ptr<Pass> make_split_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
                                       bool scale_inverse, HalfMode half = HALF_NONE);
+// runtime-length pass with compile-time codelets (rt.cu): any stage list with radices <= 32, f32 output
+std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
+                                   bool scale_inverse, HalfMode half = HALF_NONE);
 // fused N-d kernel (fused_registry.cu): one pass object that replaces ALL per-axis passes, or nullptr
 std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan);
 

@@ -56,7 +56,7 @@ def test_published_4d_5d_shapes():
 
 
 def test_split_respects_user_bases():
-    """Bases that cannot be grouped into any (N1, N2) kernel pair fall back to the generic kernel."""
+    """Bases that cannot be grouped into any (N1, N2) kernel pair fall back to the runtime-length / generic kernels."""
     rel, mx, desc = _run((2, 1920, 64), bases=[[64, 30], [64]])      # 64*30: no such pair registered
     assert "split" not in desc.split("\n")[1] and rel < 2e-6, desc
     rel, mx, desc = _run((2, 1920, 64), bases=[[16, 8, 15], [8, 8]])  # groupable into (16,8) x (15)
