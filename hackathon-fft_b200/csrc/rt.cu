@@ -96,7 +96,8 @@ struct RtPass : Pass {
 std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
                                    bool scale_inverse, HalfMode half) {
   const Problem& p = plan.prob;
-  if (half != HALF_NONE || p.desc.out_dtype != B200FFT_F32 || view.n > (1 << 20)) return nullptr;
+  if (p.desc.out_dtype != B200FFT_F32 || view.n > (1 << 20)) return nullptr;
+  if (half != HALF_NONE && view.inner != 1) return nullptr;  // half-spectrum handling is a row pass
   const AxisSpec& ax = p.axes[axis];
   std::vector<int> radices;
   if (!group_stages(ax.ordered, &radices)) return nullptr;
@@ -112,8 +113,9 @@ std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView&
   a.inner = view.inner;
   a.in_dtype = src.dtype;
   a.in_comps = src.comps;
-  a.do_scale = scale_inverse ? 1 : 0;
-  a.scale = scale_inverse ? (float)(1.0 / (double)n) : 1.f;
+  a.half = (int)half;
+  a.do_scale = (scale_inverse || half == HALF_C2R) ? 1 : 0;  // the half-spectrum inverse is always normalised
+  a.scale = a.do_scale ? (float)(1.0 / (double)n) : 1.f;
   // tile: ~4096 points per CTA for rows (at least enough butterflies for the threads), 16 columns for strided axes
   int tile;
   if (a.row) {
@@ -165,7 +167,8 @@ std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView&
   char buf[320];
   snprintf(buf, sizeof buf, "axis %d: rt_%s n=%d inner=%lld tile=%d smem=%zuB user stages=[%s] fused as (%s)%s", axis,
            a.row ? "rows" : "cols", n, (long long)view.inner, tile, pass->smem, stages.c_str(), radix_name(radices).c_str(),
-           src.comps == 1 ? " real-in" : "");
+           half == HALF_R2C ? " r2c (n-point, bins 0..n/2 stored)" : half == HALF_C2R ? " c2r (Hermitian load)"
+                                                                                       : src.comps == 1 ? " real-in" : "");
   pass->text = buf;
   return pass;
 }

@@ -23,6 +23,8 @@ struct RtArgs {
   int n, nstages, tile;   // tile = rows per CTA (rows) / columns per CTA (cols)
   int row;                // 1 = contiguous rows
   int in_dtype, in_comps;
+  int half;               // rows only. 1 (R2C): real rows in, bins 0..n/2 out with row pitch n/2+1. 2 (C2R): rows of
+                          // n/2+1 bins in, Hermitian-extended on load (X[n-k] = conj X[k]), real rows out.
   int radix[RT_MAX_STAGES];
   int tw_off[RT_MAX_STAGES];
   int stride[RT_MAX_STAGES];  // rows: padded row pitch of the exchange written by stage s
@@ -54,7 +56,20 @@ __device__ __forceinline__ void rt_stage(const RtArgs& a, const RtTile& t, int s
     const int n = qn % NB, o = qn / NB;
     const int p = n % P, g = n / P;
     float2 x[R];
-    if (first) {
+    if (first && a.half == 2) {
+      const int hb = N / 2 + 1;
+      const long long rowb = (t.gbase / N + o) * hb;  // rows: gbase = first row * N
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int i = n + j * NB;
+        float2 v = make_float2(0.f, 0.f);
+        if (o < t.valid_o) {
+          v = load_any<float>(a.in, a.in_dtype, 2, rowb + (i < hb ? i : N - i));
+          if (i >= hb) v.y = -v.y;
+        }
+        x[j] = v;
+      }
+    } else if (first) {
       const bool ok = o < t.valid_o && c < t.valid_c;
 #pragma unroll
       for (int j = 0; j < R; ++j)
@@ -74,7 +89,23 @@ __device__ __forceinline__ void rt_stage(const RtArgs& a, const RtTile& t, int s
       for (int j = 1; j < R; ++j) x[j] = cmulf(x[j], __ldg(&tw[(j - 1) * P + p]));
     }
     Dft<R, INV>::run(x);
-    if (last) {
+    if (last && a.half != 0) {
+      if (o < t.valid_o) {
+        const int hb = N / 2 + 1;
+        const long long row = t.gbase / N + o;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int i = g * Q + p + k * P;
+          float2 v = x[k];
+          if (a.do_scale) { v.x *= a.scale; v.y *= a.scale; }
+          if (a.half == 1) {
+            if (i < hb) a.out[row * hb + i] = v;
+          } else {
+            reinterpret_cast<float*>(a.out)[row * N + i] = v.x;
+          }
+        }
+      }
+    } else if (last) {
       if (o < t.valid_o && c < t.valid_c) {
         float2* __restrict__ dst = a.out + t.gbase + o * t.so + c;
 #pragma unroll

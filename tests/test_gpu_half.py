@@ -135,3 +135,17 @@ def test_f64_and_errors():
     with pytest.raises(b200fft.B200FFTError) as e:     # wrong number of bins for the real length
         b200fft.plan_fft("float32", "float32", (2, 93, 1), (2, 46, 2), real_mode=b200fft.REAL_HALF)
     assert e.value.status == 2
+
+
+def test_unregistered_lengths_use_the_rt_tier():
+    """Half-spectrum rows without a fused R2C/C2R kernel (odd or unregistered lengths) run on the runtime-length
+    tier (n-point transform, bins 0..n/2 stored / Hermitian-extended load), not on the generic kernel."""
+    rng = np.random.default_rng(4)
+    for shape in ((6, 93), (3, 1000), (2, 12, 30)):
+        x = rng.standard_normal(shape + (1,)).astype(np.float32)
+        got, desc = r2c(x)
+        assert "rt_rows" in desc and "generic" not in desc, desc
+        want = np.fft.rfftn(x[..., 0].astype(np.float64), axes=tuple(range(1, len(shape))))
+        assert np.linalg.norm(c2(got) - want) <= 2e-6 * np.sqrt(len(shape) - 1) * np.linalg.norm(want)
+        back, _ = c2r(got, shape[-1])
+        assert np.linalg.norm(back[..., 0] - x[..., 0]) <= 4e-6 * np.linalg.norm(x)
