@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,6 +45,27 @@ void register_all_fused() {
   register_fused_async_2d();
   register_fused_3d();
   register_fused_2d();
+}
+
+// Two persistent kernels with STATIC work assignment (fused2.cuh) must not share the SMs: each sizes its grid
+// to the whole device, and with both only partly resident the resident CTAs of each could spin on tiles owned by
+// CTAs that cannot be scheduled. Launches of such kernels are therefore chained device-wide (all streams of this
+// process) through one event per device; kernels with dynamic in-order work fetch (fused.cuh, slab.cuh) do not
+// need it. B200FFT_FUSED_SERIALIZE=0 disables the chaining (e.g. for CUDA-graph capture of a single stream).
+struct FusedChain {
+  std::mutex mu;
+  cudaEvent_t ev[64] = {};
+};
+FusedChain& fused_chain() {
+  static FusedChain c;
+  return c;
+}
+bool fused_serialize() {
+  static const bool on = [] {
+    const char* e = getenv("B200FFT_FUSED_SERIALIZE");
+    return !e || atoi(e) != 0;
+  }();
+  return on;
 }
 
 long long prod(const std::vector<long long>& v, size_t a, size_t b) {
@@ -120,7 +142,18 @@ struct FusedPass : Pass {
         if (!encode_axis_map(&maps[q], dst, geom[q].inner, geom[q].n, geom[q].outer_per_batch * nbatch, geom[q].cw,
                              geom[q].box_rows))
           return fail(B200FFT_ERR_CUDA, "cuTensorMapEncodeTiled failed for phase %d of %s", q, v->name.c_str());
-      v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
+      cudaEvent_t chain = nullptr;
+      if (fused_serialize() && plan->device >= 0 && plan->device < 64) {
+        FusedChain& fc = fused_chain();
+        std::lock_guard<std::mutex> lock(fc.mu);
+        if (!fc.ev[plan->device]) cudaEventCreateWithFlags(&fc.ev[plan->device], cudaEventDisableTiming);
+        chain = fc.ev[plan->device];
+        if (chain) cudaStreamWaitEvent(stream, chain, 0);  // after the previous statically scheduled kernel
+        v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
+        if (chain) cudaEventRecord(chain, stream);
+      } else {
+        v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
+      }
     } else {
       v->launch(a, grid, v->smem, stream);
     }

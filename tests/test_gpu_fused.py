@@ -142,3 +142,21 @@ def test_fused_through_exec_host():
     plan.exec_host(h_out.numpy(), h_in.numpy())
     want = _ref(x.cuda())
     _check(h_out.cuda(), want)
+
+
+def test_two_fused_plans_on_two_streams():
+    """Statically scheduled persistent kernels are chained device-wide, so two plans launched back to back on
+    different streams cannot starve each other of SMs (each grid is sized to the whole device)."""
+    import torch
+    xs = [torch.randn((40, 64, 64, 64, 2), device="cuda") for _ in range(2)]
+    outs = [torch.empty_like(x) for x in xs]
+    plans = [b200fft.plan_fft("float32", "float32", x.shape, x.shape) for x in xs]
+    assert all(p.describe().startswith("fused ndA") for p in plans)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for _ in range(20):
+        for p, x, o, st in zip(plans, xs, outs, streams):
+            p.exec(o, x, st.cuda_stream)
+    torch.cuda.synchronize()
+    for x, o in zip(xs, outs):
+        _check(o, _ref(x))
