@@ -62,6 +62,15 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Spin until *cnt >= want. Every tile only waits for tiles that were handed out earlier, so the wait always ends;
+// should a bug ever break that, the kernel traps after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void wait_counter_gpu(const unsigned* cnt, unsigned want, unsigned sleep_ns) {
+  unsigned spins = 0;
+  while (ld_acquire_gpu(cnt) < want) {
+    __nanosleep(sleep_ns);
+    if (++spins > 30000000u) __trap();
+  }
+}
 
 // ---- phases: the tile bodies of fast.cuh as device functions --------------------------------------
 enum NdKind { ND_NONE = 0, ND_ROWS = 1, ND_COLS = 2, ND_R2C = 3, ND_PLANE = 4 };
@@ -192,7 +201,7 @@ __device__ __forceinline__ void nd_do_phase(const NdArgs& a, long long gtile, fl
       const NdPhase& Q = a.ph[PH - 1];
       const unsigned* cnt = a.ctrl + a.cnt_off[PH - 1] + t * Q.groups_per_transform + tile / P.dep_div;
       const unsigned want = (unsigned)Q.tiles_per_group;
-      while (ld_acquire_gpu(cnt) < want) __nanosleep(64);
+      wait_counter_gpu(cnt, want, 64);
     }
     __syncthreads();
   }

@@ -382,8 +382,7 @@ __global__ void __launch_bounds__(NT + 32, MINB)
           tma::mbar_arrive(&full[slot]);
           break;
         }
-        if (!r.ready)
-          while (ld_acquire_gpu(r.cnt) < r.want) __nanosleep(32);
+        if (!r.ready) wait_counter_gpu(r.cnt, r.want, 32);
         if (r.phase > 0) tma::fence_proxy_async_all();
         void* in_buf = base + slot * IN;
         if (r.phase == 0) nd_issue<0, P0>(a, nullptr, r, in_buf, &full[slot], &ring[slot]);

@@ -126,8 +126,7 @@ __global__ void __launch_bounds__(NT, 2) slab_fused_kernel(const __grid_constant
       __syncthreads();
       if (!s_ready) {
         flush_signal();  // never spin while holding a signal somebody may be waiting for
-        if (threadIdx.x == 0)
-          while (ld_acquire_gpu(a.ctrl + 2 + z) < (unsigned)ROW_TILES_PER_PLANE) __nanosleep(64);
+        if (threadIdx.x == 0) wait_counter_gpu(a.ctrl + 2 + z, (unsigned)ROW_TILES_PER_PLANE, 64);
         __syncthreads();
       }
       const long long base = (long long)z * NY * NX + (long long)b * CW;

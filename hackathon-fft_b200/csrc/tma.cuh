@@ -20,9 +20,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Bounded: a wait that can never complete (a lost arrival = a bug) traps after ~10^8 polls instead of hanging the
+// GPU; the kernel then ends with an error the host sees at the next synchronisation.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
+  uint32_t polls = 0;
   do {
+    if (++polls > 100000000u) __trap();
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
