@@ -26,45 +26,39 @@ namespace b200fft {
 
 namespace {
 
-// contiguous partition of the ordered stage list into the fewest groups of product <= RT_MAX_RADIX, ties broken by
-// the smallest maximum group (balanced super-stages)
+// Group the ordered stage list (a multiset of bases whose product is N) into the fewest super-stages of product
+// <= RT_MAX_RADIX, balanced: bases in descending order, each to the currently smallest group that still has room
+// (longest-processing-time rule). 100 = [5,5,2,2] -> (10)(10); 1000 -> (10)(10)(10); 243 = [3]x5 -> (27)(9).
 bool group_stages(const std::vector<uint32_t>& ordered, std::vector<int>* out) {
-  const size_t m = ordered.size();
   for (uint32_t r : ordered)
     if (r > (uint32_t)RT_MAX_RADIX) return false;
-  std::vector<int> best;
-  int best_max = 1 << 30;
-  std::vector<int> cur;
-  for (int want = 1; want <= RT_MAX_STAGES && best.empty(); ++want) {
-    std::function<void(size_t, int)> rec = [&](size_t i, int left) {
-      if (i == m) {
-        if (left == 0) {
-          const int mx = *std::max_element(cur.begin(), cur.end());
-          if (mx < best_max) { best_max = mx; best = cur; }
-        }
-        return;
-      }
-      if (left == 0) return;
-      long long prod = 1;
-      for (size_t j = i; j < m; ++j) {
-        prod *= ordered[j];
-        if (prod > RT_MAX_RADIX) break;
-        cur.push_back((int)prod);
-        rec(j + 1, left - 1);
-        cur.pop_back();
-      }
-    };
-    rec(0, want);
+  std::vector<uint32_t> bases(ordered);
+  std::sort(bases.begin(), bases.end(), [](uint32_t x, uint32_t y) { return x > y; });
+  for (int want = 1; want <= RT_MAX_STAGES; ++want) {
+    std::vector<long long> g((size_t)want, 1);
+    bool ok = true;
+    for (uint32_t b : bases) {
+      int best = -1;
+      for (int i = 0; i < want; ++i)
+        if (g[i] * b <= RT_MAX_RADIX && (best < 0 || g[i] < g[best])) best = i;
+      if (best < 0) { ok = false; break; }
+      g[best] *= b;
+    }
+    if (!ok) continue;
+    std::sort(g.begin(), g.end(), [](long long x, long long y) { return x > y; });  // largest radix first
+    out->clear();
+    for (long long v : g)
+      if (v > 1) out->push_back((int)v);
+    if (out->empty()) out->push_back(1);
+    return true;
   }
-  if (best.empty()) return false;
-  *out = best;
-  return true;
+  return false;
 }
 
 struct RtPass : Pass {
   RtArgs base;
   AxisView view;
-  bool inverse = false;
+  bool inverse = false, small = false;
   size_t smem = 0;
   int sm_count = 148;
   std::string text;
@@ -83,7 +77,7 @@ struct RtPass : Pass {
     }
     if (a.ntiles <= 0) return B200FFT_OK;
     const unsigned grid = (unsigned)std::min<long long>(a.ntiles, (long long)sm_count * 32);
-    rt_launch(inverse, a, grid, smem, stream);
+    rt_launch(inverse, small, a, grid, smem, stream);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     B200_CUDA_CHECK(cudaGetLastError());
     return B200FFT_OK;
@@ -117,13 +111,16 @@ std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView&
   a.do_scale = (scale_inverse || half == HALF_C2R) ? 1 : 0;  // the half-spectrum inverse is always normalised
   a.scale = a.do_scale ? (float)(1.0 / (double)n) : 1.f;
   // tile: ~4096 points per CTA for rows (at least enough butterflies for the threads), 16 columns for strided axes
-  int tile;
+  // tile: enough sub-transforms that the stage with the largest radix (fewest butterflies) still gives every
+  // thread about two butterflies; strided axes take at least 16 columns (128 contiguous bytes per row)
+  const int rmax = *std::max_element(radices.begin(), radices.end());
+  int tile = (int)((2LL * RT_THREADS * rmax + n - 1) / n);
   if (a.row) {
-    tile = std::max(1, 4096 / n);
-    const int min_radix = *std::min_element(radices.begin(), radices.end());
-    (void)min_radix;
+    tile = std::max(1, tile);
   } else {
-    tile = (int)std::min<long long>(16, view.inner);
+    tile = std::max(16, (tile + 7) / 8 * 8);
+    tile = (int)std::min<long long>(tile, (view.inner + 7) / 8 * 8);
+    tile = std::max(1, tile);
   }
   // exchange geometry
   long long P = 1;
@@ -143,16 +140,26 @@ std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView&
   }
   const size_t nbuf = S > 2 ? 2 : (S > 1 ? 1 : 0);
   auto smem_for = [&](int t) { return nbuf * (size_t)(a.row ? (size_t)t * max_stride : (size_t)n * t) * sizeof(float2); };
-  while (tile > 1 && smem_for(tile) > 160 * 1024) tile /= 2;
+  while (tile > 1 && smem_for(tile) > 100 * 1024) tile = (tile + 1) / 2;  // two CTAs per SM when possible
   if (smem_for(tile) > 227 * 1024) return nullptr;  // too long for one tile: split_registry / generic decide
   a.tile = tile;
   a.tiles_per_outer = a.row ? 1 : (int)((view.inner + tile - 1) / tile);
   a.buf_elems = (int)(a.row ? (size_t)tile * max_stride : (size_t)n * tile);
+  {
+    long long PP = 1;
+    for (int s2 = 0; s2 < S; ++s2) {
+      a.div_nb[s2].set((unsigned)(n / radices[s2]));
+      a.div_p[s2].set((unsigned)PP);
+      PP *= radices[s2];
+    }
+    a.div_cn.set((unsigned)(a.row ? 1 : tile));
+  }
   pass->smem = smem_for(tile);
   pass->view = view;
   pass->inverse = p.desc.inverse != 0;
   pass->sm_count = plan.sm_count;
-  if (rt_prepare(pass->inverse, 227 * 1024) != cudaSuccess) {
+  pass->small = rmax <= 16;
+  if (rt_prepare(pass->inverse, pass->small, 227 * 1024) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }

@@ -1,5 +1,5 @@
 // Kernel of the runtime-length tier (see rt.cu). Included by rt.cu (host side) and by the two instantiation
-// units rt_inst_fwd.cu / rt_inst_inv.cu (31 codelets per direction: compiled in parallel).
+// units rt_inst_{fwd,inv}_{small,large}.cu (compiled in parallel).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -11,6 +11,25 @@ namespace b200fft {
 constexpr int RT_MAX_STAGES = 6;
 constexpr int RT_THREADS = 256;
 constexpr int RT_MAX_RADIX = 32;
+
+// q / d for 0 <= q < 2^31 with host-prepared constants (d >= 1): one multiply-high and a shift instead of the
+// ~25-instruction integer division, three of which were needed per butterfly
+struct RtDiv {
+  unsigned mul, shift, d;
+  __host__ void set(unsigned dd) {
+    d = dd;
+    if (dd <= 1) { mul = 0; shift = 0; return; }
+    unsigned l = 0;
+    while ((1ull << l) < dd) ++l;                    // ceil(log2 d)
+    mul = (unsigned)(((1ull << 32) * ((1ull << l) - dd)) / dd + 1);
+    shift = l;
+  }
+  __device__ __forceinline__ unsigned div(unsigned q) const {
+    if (d <= 1) return q;
+    const unsigned t = __umulhi(q, mul);
+    return (t + ((q - t) >> 1)) >> (shift - 1);
+  }
+};
 
 struct RtArgs {
   const void* in;
@@ -30,6 +49,9 @@ struct RtArgs {
   int stride[RT_MAX_STAGES];  // rows: padded row pitch of the exchange written by stage s
   int padP[RT_MAX_STAGES];    // rows: pad of P elements per Q-block after stage s (0 = dense)
   int buf_elems;              // elements of one exchange buffer
+  RtDiv div_nb[RT_MAX_STAGES];  // by NB = n / R_s
+  RtDiv div_p[RT_MAX_STAGES];   // by P_s
+  RtDiv div_cn;                 // by the number of columns per tile (cols)
   float scale;
   int do_scale;
 };
@@ -51,10 +73,12 @@ __device__ __forceinline__ void rt_stage(const RtArgs& a, const RtTile& t, int s
   const int in_stride = first ? 0 : a.stride[s - 1], in_pad = first ? 0 : a.padP[s - 1];
   const int out_stride = last ? 0 : a.stride[s], out_pad = last ? 0 : a.padP[s];
   for (int q = threadIdx.x; q < total; q += RT_THREADS) {
-    const int c = t.CN == 1 ? 0 : q % t.CN;
-    const int qn = t.CN == 1 ? q : q / t.CN;
-    const int n = qn % NB, o = qn / NB;
-    const int p = n % P, g = n / P;
+    const int qn = t.CN == 1 ? q : (int)a.div_cn.div((unsigned)q);
+    const int c = t.CN == 1 ? 0 : q - qn * t.CN;
+    const int o = t.O == 1 ? 0 : (int)a.div_nb[s].div((unsigned)qn);
+    const int n = qn - o * NB;
+    const int g = (int)a.div_p[s].div((unsigned)n);
+    const int p = n - g * P;
     float2 x[R];
     if (first && a.half == 2) {
       const int hb = N / 2 + 1;
@@ -71,13 +95,20 @@ __device__ __forceinline__ void rt_stage(const RtArgs& a, const RtTile& t, int s
       }
     } else if (first) {
       const bool ok = o < t.valid_o && c < t.valid_c;
+      const long long e0 = t.gbase + o * t.so + (long long)n * t.si + c;
+      const long long ej = (long long)NB * t.si;
+      if (a.in_dtype == B200FFT_F32 && a.in_comps == 2) {  // the common case without the per-element type switch
+        const float2* __restrict__ src = reinterpret_cast<const float2*>(a.in);
 #pragma unroll
-      for (int j = 0; j < R; ++j)
-        x[j] = ok ? load_any<float>(a.in, a.in_dtype, a.in_comps, t.gbase + o * t.so + (long long)(n + j * NB) * t.si + c)
-                  : make_float2(0.f, 0.f);
+        for (int j = 0; j < R; ++j) x[j] = ok ? __ldg(src + e0 + j * ej) : make_float2(0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          x[j] = ok ? load_any<float>(a.in, a.in_dtype, a.in_comps, e0 + j * ej) : make_float2(0.f, 0.f);
+      }
     } else if (t.CN == 1) {
       // element n + j*NB of row o; its Q-block in the previous exchange is (n + j*NB) / P = g + j*(NB/P)
-      const int blocks = NB / P;
+      const int blocks = in_pad ? (int)a.div_p[s].div((unsigned)NB) : 0;
 #pragma unroll
       for (int j = 0; j < R; ++j) x[j] = cur[o * in_stride + n + j * NB + (g + j * blocks) * in_pad];
     } else {
@@ -125,8 +156,11 @@ __device__ __forceinline__ void rt_stage(const RtArgs& a, const RtTile& t, int s
   }
 }
 
-template <bool INV>
-__global__ void __launch_bounds__(RT_THREADS) rt_axis_kernel(const __grid_constant__ RtArgs a) {
+// RMAXK = 16: codelets up to radix 16 only (128 registers without spills); RMAXK = 32: all codelets, also held to
+// 128 registers — the radix-27..32 codelets then spill ~2 KB, which measured FASTER than 246 registers at one CTA
+// per SM (50000 x 1000: 0.51 vs 0.82 ms). The planner picks by the largest super-stage of the axis.
+template <bool INV, int RMAXK>
+__global__ void __launch_bounds__(RT_THREADS, 2) rt_axis_kernel(const __grid_constant__ RtArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + a.buf_elems;
@@ -157,7 +191,10 @@ __global__ void __launch_bounds__(RT_THREADS) rt_axis_kernel(const __grid_consta
       const float2* cur = (s % 2 == 1) ? buf0 : buf1;  // stage s reads what stage s-1 wrote
       float2* nxt = (s % 2 == 0) ? buf0 : buf1;
       switch (a.radix[s]) {
-#define B200_RT_CASE(R) case R: rt_stage<R, INV>(a, t, s, P, cur, nxt); break;
+#define B200_RT_CASE(R) \
+  case R:               \
+    if constexpr (R <= RMAXK) rt_stage<R, INV>(a, t, s, P, cur, nxt); \
+    break;
         B200_RT_CASE(2) B200_RT_CASE(3) B200_RT_CASE(4) B200_RT_CASE(5) B200_RT_CASE(6) B200_RT_CASE(7) B200_RT_CASE(8)
         B200_RT_CASE(9) B200_RT_CASE(10) B200_RT_CASE(11) B200_RT_CASE(12) B200_RT_CASE(13) B200_RT_CASE(14)
         B200_RT_CASE(15) B200_RT_CASE(16) B200_RT_CASE(17) B200_RT_CASE(18) B200_RT_CASE(19) B200_RT_CASE(20)
@@ -173,14 +210,21 @@ __global__ void __launch_bounds__(RT_THREADS) rt_axis_kernel(const __grid_consta
 }
 
 // defined in rt_inst_fwd.cu / rt_inst_inv.cu
-void rt_launch_fwd(const RtArgs& a, unsigned grid, size_t smem, cudaStream_t stream);
-void rt_launch_inv(const RtArgs& a, unsigned grid, size_t smem, cudaStream_t stream);
-cudaError_t rt_prepare_fwd(int max_smem);
-cudaError_t rt_prepare_inv(int max_smem);
-inline void rt_launch(bool inverse, const RtArgs& a, unsigned grid, size_t smem, cudaStream_t stream) {
-  if (inverse) rt_launch_inv(a, grid, smem, stream);
-  else rt_launch_fwd(a, grid, smem, stream);
+void rt_launch_fwd_small(const RtArgs& a, unsigned grid, size_t smem, cudaStream_t stream);
+void rt_launch_fwd_large(const RtArgs& a, unsigned grid, size_t smem, cudaStream_t stream);
+void rt_launch_inv_small(const RtArgs& a, unsigned grid, size_t smem, cudaStream_t stream);
+void rt_launch_inv_large(const RtArgs& a, unsigned grid, size_t smem, cudaStream_t stream);
+cudaError_t rt_prepare_fwd_small(int max_smem);
+cudaError_t rt_prepare_fwd_large(int max_smem);
+cudaError_t rt_prepare_inv_small(int max_smem);
+cudaError_t rt_prepare_inv_large(int max_smem);
+inline void rt_launch(bool inverse, bool small, const RtArgs& a, unsigned grid, size_t smem, cudaStream_t stream) {
+  if (inverse) (small ? rt_launch_inv_small : rt_launch_inv_large)(a, grid, smem, stream);
+  else (small ? rt_launch_fwd_small : rt_launch_fwd_large)(a, grid, smem, stream);
 }
-inline cudaError_t rt_prepare(bool inverse, int max_smem) { return inverse ? rt_prepare_inv(max_smem) : rt_prepare_fwd(max_smem); }
+inline cudaError_t rt_prepare(bool inverse, bool small, int max_smem) {
+  if (inverse) return (small ? rt_prepare_inv_small : rt_prepare_inv_large)(max_smem);
+  return (small ? rt_prepare_fwd_small : rt_prepare_fwd_large)(max_smem);
+}
 
 }  // namespace b200fft
