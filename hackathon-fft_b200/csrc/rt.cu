@@ -140,7 +140,9 @@ std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView&
   }
   const size_t nbuf = S > 2 ? 2 : (S > 1 ? 1 : 0);
   auto smem_for = [&](int t) { return nbuf * (size_t)(a.row ? (size_t)t * max_stride : (size_t)n * t) * sizeof(float2); };
-  while (tile > 1 && smem_for(tile) > 100 * 1024) tile = (tile + 1) / 2;  // two CTAs per SM when possible
+  // two CTAs per SM when possible, but a strided tile keeps at least 8 columns (64 contiguous bytes per row)
+  const int min_tile = a.row ? 1 : (int)std::min<long long>(8, view.inner);
+  while (tile > min_tile && smem_for(tile) > 112 * 1024) tile = std::max(min_tile, (tile + 1) / 2);
   if (smem_for(tile) > 227 * 1024) return nullptr;  // too long for one tile: split_registry / generic decide
   a.tile = tile;
   a.tiles_per_outer = a.row ? 1 : (int)((view.inner + tile - 1) / tile);
