@@ -114,3 +114,23 @@ def test_no_cpu_fallback():
     with pytest.raises(b200fft.B200FFTError) as e:
         b200fft.plan_fft("float32", "float32", (2, 8, 2), (2, 8, 2))
     assert e.value.status == 5
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/b200fft.h must be consumable from C (the Mojo / cgo-style FFI boundary): compile a C99 program against
+    it with gcc -pedantic, link it with the built library and call two entry points that need no GPU."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "b200fft.h"\n#include <string.h>\n'
+                   "int main(void) {\n"
+                   "  uint32_t out[16]; uint32_t bases[1] = {2};\n"
+                   "  b200fft_desc d; memset(&d, 0, sizeof d);\n"
+                   "  if (sizeof(b200fft_desc) != 128) return 2;\n"
+                   "  if (b200fft_version() <= 0) return 3;\n"
+                   "  if (b200fft_ordered_bases(8, bases, 1, out, 16) != 3) return 4;\n"
+                   "  return strcmp(b200fft_strerror(B200FFT_OK), \"ok\") != 0;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(b200fft.lib_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lb200fft", "-Wl,-rpath," + libdir])
+    assert subprocess.run([str(exe)]).returncode == 0
