@@ -277,6 +277,9 @@ int b200fft_plan_create(b200fft_plan** out, const b200fft_desc* desc) {
   }
   rc = build_passes(plan.get(), /*dry=*/false, nullptr);
   if (rc != B200FFT_OK) { b200fft_plan_destroy(plan.release()); return rc; }
+  // The tables were uploaded with cudaMemcpy from pageable memory on the legacy stream: make sure they have landed
+  // before the caller launches on a non-blocking stream of its own (which is not ordered after the legacy stream).
+  B200_CUDA_CHECK(cudaDeviceSynchronize());
   *out = plan.release();
   return B200FFT_OK;
 }

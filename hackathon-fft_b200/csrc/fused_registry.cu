@@ -115,6 +115,9 @@ struct FusedPass : Pass {
     plan->owned_device.push_back(pb.d_ctrl);
     B200_CUDA_CHECK(cudaMemcpy(pb.d_segs, segs.data(), sizeof(NdSegment) * segs.size(), cudaMemcpyHostToDevice));
     B200_CUDA_CHECK(cudaMemset(pb.d_ctrl, 0, sizeof(unsigned) * (size_t)pb.nwords));
+    // one-time, per batch count: the schedule and the zeroed counters must be in place before the kernel runs on
+    // the caller's stream, which need not be ordered after the legacy stream used above
+    B200_CUDA_CHECK(cudaDeviceSynchronize());
     auto ins = per_batch.emplace(nbatch, pb);
     *out = &ins.first->second;
     return B200FFT_OK;

@@ -152,6 +152,11 @@ int b200fft_slab_create(b200fft_slab** out, int64_t n, int ranks, int rank, int 
     return fail(B200FFT_ERR_CUDA, "fused slab kernel does not fit an SM");
   }
   s->grid = occ * prop.multiProcessorCount;
+  if (cudaDeviceSynchronize() != cudaSuccess) {  // tables, schedule and zeroed counters are in place before any exec
+    cudaGetLastError();
+    b200fft_slab_destroy(s.release());
+    return fail(B200FFT_ERR_CUDA, "device synchronisation failed while creating the slab plan");
+  }
   char buf[256];
   snprintf(buf, sizeof buf, "slab_fused %d^3 rank %d/%d (%s per axis): rows c%d -> cols w%d + scatter -> cols w%d; grid %d x %d, smem=%zuB, z delay=%d blocks",
            s->n, rank, ranks, radix_name(s->radices).c_str(), s->c, s->cw, s->cw, s->grid, s->threads, s->smem, delay);
