@@ -214,6 +214,9 @@ struct AxisPlan {
   std::vector<u64> radix, processed;
   std::vector<Cx<T>> tw;  // W_N^n, n in [0, N)
   bool unrolled;          // N <= MAX_STACK_SEQ_LEN (128): comptime path
+  // per-stage copy of the twiddles in the order the stage walks them, stw[s][(j-1)*Q + u] = W[((j*u) mod Q)*rho]:
+  // the same values as the gather from `tw`, laid out contiguously so the vector path below can load them
+  std::vector<std::vector<Cx<T>>> stw;
 };
 
 // Source of a stage: either the typed user input (stage 0 of the last axis) or
@@ -269,6 +272,96 @@ void run_stage_impl(const AxisPlan<T>& ax, size_t s, bool inverse, Getter get, C
   }
 }
 
+#if defined(__AVX2__) && defined(__FMA__)
+}  // namespace
+#include <immintrin.h>
+namespace {
+// Vector form of one runtime-path stage (float, complex source, P >= 4): four output points per iteration.
+// Every lane performs exactly the scalar sequence of cfma() — fma(w.re, x.re, fma(-w.im, x.im, acc.re)) and
+// fma(w.re, x.im, fma(w.im, x.re, acc.im)) — so the results are bit-identical to run_stage_impl; it only makes the
+// CPU baseline run at the speed a SIMD implementation like the reference's reaches.
+inline bool run_stage_f32_avx2(const AxisPlan<float>& ax, size_t s, bool inverse, const Cx<float>* x, Cx<float>* out) {
+  const u64 N = ax.N, r = ax.radix[s], P = ax.processed[s], Q = P * r, step = N / r;
+  if (ax.unrolled || s >= ax.stw.size() || ax.stw[s].empty()) return false;
+  const bool scale = inverse && (Q == N);
+  if (P < 4) {
+    // P = 1 or 2 (the first stages): the inputs x[m + j*step], m = q*P + p, are contiguous in m, the twiddle
+    // pattern has period P, and the four results go to out[(m / P)*Q + k*P + m % P]: P-element pieces, Q apart.
+    if ((P != 1 && P != 2) || (N / r) % 4 != 0) return false;
+    const __m256 vinv1 = _mm256_set1_ps((float)(1.0 / (double)N));
+    const __m256 sgn = _mm256_castsi256_ps(_mm256_set_epi32(0, (int)0x80000000, 0, (int)0x80000000, 0, (int)0x80000000, 0,
+                                                            (int)0x80000000));
+    const Cx<float>* stw1 = ax.stw[s].data();
+    for (u64 k = 0; k < r; ++k) {
+      // 4-wide twiddle vectors for this k: lanes m % P select u = k*P + p
+      alignas(32) Cx<float> wl[32][4];
+      for (u64 j = 1; j < r && j < 32; ++j)
+        for (int l = 0; l < 4; ++l) wl[j][l] = stw1[(j - 1) * Q + k * P + (u64)l % P];
+      if (r > 32) return false;
+      for (u64 m = 0; m < N / r; m += 4) {
+        __m256 acc = _mm256_loadu_ps(reinterpret_cast<const float*>(x + m));
+        for (u64 j = 1; j < r; ++j) {
+          const __m256 w = _mm256_load_ps(reinterpret_cast<const float*>(wl[j]));
+          const __m256 xv = _mm256_loadu_ps(reinterpret_cast<const float*>(x + m + j * step));
+          const __m256 wre = _mm256_moveldup_ps(w), wim = _mm256_movehdup_ps(w);
+          const __m256 xs = _mm256_permute_ps(xv, 0xB1);
+          const __m256 t = _mm256_fmadd_ps(_mm256_xor_ps(wim, sgn), xs, acc);
+          acc = _mm256_fmadd_ps(wre, xv, t);
+        }
+        if (scale) acc = _mm256_mul_ps(acc, vinv1);
+        alignas(32) Cx<float> res[4];
+        _mm256_store_ps(reinterpret_cast<float*>(res), acc);
+        for (int l = 0; l < 4; ++l) {
+          const u64 mm = m + (u64)l;
+          out[(mm / P) * Q + k * P + mm % P] = res[l];
+        }
+      }
+    }
+    return true;
+  }
+  const float inv_n = (float)(1.0 / (double)N);
+  const __m256 vinv = _mm256_set1_ps(inv_n);
+  const __m256 sign_even = _mm256_castsi256_ps(_mm256_set_epi32(0, (int)0x80000000, 0, (int)0x80000000, 0, (int)0x80000000, 0,
+                                                                (int)0x80000000));
+  const Cx<float>* stw = ax.stw[s].data();
+  const u64 P4 = P & ~(u64)3;
+  for (u64 q = 0; q < N / Q; ++q) {
+    for (u64 k = 0; k < r; ++k) {
+      const u64 i0 = q * Q + k * P, n0 = q * P, u0 = k * P;
+      for (u64 p = 0; p < P4; p += 4) {
+        __m256 acc = _mm256_loadu_ps(reinterpret_cast<const float*>(x + n0 + p));
+        for (u64 j = 1; j < r; ++j) {
+          const __m256 w = _mm256_loadu_ps(reinterpret_cast<const float*>(stw + (j - 1) * Q + u0 + p));
+          const __m256 xv = _mm256_loadu_ps(reinterpret_cast<const float*>(x + n0 + p + j * step));
+          const __m256 wre = _mm256_moveldup_ps(w), wim = _mm256_movehdup_ps(w);
+          const __m256 xs = _mm256_permute_ps(xv, 0xB1);  // (im, re) pairs
+          const __m256 t = _mm256_fmadd_ps(_mm256_xor_ps(wim, sign_even), xs, acc);
+          acc = _mm256_fmadd_ps(wre, xv, t);
+        }
+        if (scale) acc = _mm256_mul_ps(acc, vinv);
+        _mm256_storeu_ps(reinterpret_cast<float*>(out + i0 + p), acc);
+      }
+      for (u64 p = P4; p < P; ++p) {
+        Cx<float> acc = x[n0 + p];
+        for (u64 j = 1; j < r; ++j) acc = cfma(stw[(j - 1) * Q + u0 + p], x[n0 + p + j * step], acc);
+        if (scale) { acc.re *= inv_n; acc.im *= inv_n; }
+        out[i0 + p] = acc;
+      }
+    }
+  }
+  return true;
+}
+template <class T>
+inline bool run_stage_simd(const AxisPlan<T>&, size_t, bool, const Cx<T>*, Cx<T>*) { return false; }
+template <>
+inline bool run_stage_simd<float>(const AxisPlan<float>& ax, size_t s, bool inverse, const Cx<float>* x, Cx<float>* out) {
+  return run_stage_f32_avx2(ax, s, inverse, x, out);
+}
+#else
+template <class T>
+inline bool run_stage_simd(const AxisPlan<T>&, size_t, bool, const Cx<T>*, Cx<T>*) { return false; }
+#endif
+
 template <class T, bool UNROLLED, bool REAL_IN, class Getter>
 void run_stage_radix(const AxisPlan<T>& ax, size_t s, bool inverse, Getter get, Cx<T>* out) {
   switch (ax.radix[s]) {
@@ -286,6 +379,7 @@ template <class T>
 void run_stage(const AxisPlan<T>& ax, size_t s, bool inverse, const Src<T>& x, Cx<T>* out) {
   if (x.c) {  // working-dtype complex buffer: the common case
     const Cx<T>* c = x.c;
+    if (run_stage_simd<T>(ax, s, inverse, c, out)) return;
     auto get = [c](u64 i) { return c[i]; };
     if (ax.unrolled) run_stage_radix<T, true, false>(ax, s, inverse, get, out);
     else run_stage_radix<T, false, false>(ax, s, inverse, get, out);
@@ -293,6 +387,7 @@ void run_stage(const AxisPlan<T>& ax, size_t s, bool inverse, const Src<T>& x, C
   }
   if (x.comps == 2 && x.dt == (sizeof(T) == 4 ? IN_F32 : IN_F64)) {  // complex input already in T
     const Cx<T>* c = reinterpret_cast<const Cx<T>*>(x.raw);
+    if (run_stage_simd<T>(ax, s, inverse, c, out)) return;
     auto get = [c](u64 i) { return c[i]; };
     if (ax.unrolled) run_stage_radix<T, true, false>(ax, s, inverse, get, out);
     else run_stage_radix<T, false, false>(ax, s, inverse, get, out);
@@ -377,6 +472,16 @@ int exec(const void* x, int in_dtype, int in_comps, T* out_raw, int64_t batches,
       ax.unrolled = ax.N <= 128;  // _CPUPlan.MAX_STACK_SEQ_LEN
       ax.tw.resize(ax.N);
       for (u64 n = 0; n < ax.N; ++n) ax.tw[n] = twiddle<T>(n, ax.N, inverse != 0, ax.unrolled);
+      if (!ax.unrolled) {
+        ax.stw.resize(ax.radix.size());
+        for (size_t st = 0; st < ax.radix.size(); ++st) {
+          const u64 rr = ax.radix[st], PP = ax.processed[st], QQ = PP * rr, rho = ax.N / QQ;
+          if (PP == 3) continue;  // no vector path for P = 3
+          ax.stw[st].resize((size_t)((rr - 1) * QQ));
+          for (u64 j = 1; j < rr; ++j)
+            for (u64 u = 0; u < QQ; ++u) ax.stw[st][(size_t)((j - 1) * QQ + u)] = ax.tw[((j * u) % QQ) * rho];
+        }
+      }
       prod *= ax.N;
       total_stages += ax.radix.size();
       u64 mn = *std::min_element(user.begin(), user.end());
