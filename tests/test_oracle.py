@@ -118,3 +118,26 @@ def test_workers_do_not_change_result(oracle):
     a = oracle.ref_fft(x, workers=1)
     b = oracle.ref_fft(x, workers=4)
     assert np.array_equal(a, b)
+
+
+def test_simd_path_is_bit_identical_to_the_scalar_restatement(oracle, tmp_path):
+    """The oracle's AVX2 stage loops exist only to make the CPU baseline run at a realistic speed; they must give the
+    same bits as the scalar restatement of the reference (same FMA sequence per output point). Build the file once
+    more without AVX2 and compare."""
+    import ctypes
+    import subprocess
+    import importlib.util
+    src = os.path.join(os.path.dirname(oracle.__file__), "ref_fft.cpp")
+    so = str(tmp_path / "libref_scalar.so")
+    subprocess.check_call(["g++", "-O2", "-march=x86-64-v3", "-mno-avx2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-pthread",
+                           "-shared", "-o", so, src])
+    spec = importlib.util.spec_from_file_location("oracle_scalar", oracle.__file__)
+    scalar = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(scalar)
+    scalar._LIB_PATH, scalar._lib = so, None
+    rng = np.random.default_rng(12)
+    for shape, bases, inverse in [((9, 1024), None, False), ((9, 1024), None, True), ((3, 640, 480), None, False),
+                                  ((5, 1000), [[10, 10, 10]], True), ((4, 1536), [[2, 3]], False), ((2, 4096), [[16]], False),
+                                  ((6, 186), [[31, 3, 2]], False), ((7, 128), None, False)]:
+        x = rng.standard_normal(shape + (2,)).astype(np.float32)
+        assert np.array_equal(oracle.ref_fft(x, bases=bases, inverse=inverse), scalar.ref_fft(x, bases=bases, inverse=inverse)), shape
