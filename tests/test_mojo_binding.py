@@ -1,0 +1,70 @@
+"""The Mojo host package cannot be compiled in this image (no Mojo toolchain), so guard it statically: every C symbol it
+binds with external_call must be exported by the built library, its descriptor struct must list the fields of
+`struct b200fft_desc` in the header's order with matching widths, and the wrappers must keep the reference's entry-point
+names and parameter names (fft/fft/fft.mojo:160-210, 262-323)."""
+import ctypes
+import os
+import re
+
+import b200fft
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOJO = os.path.join(ROOT, "hackathon-fft_b200", "mojo", "fft")
+
+
+def _read(name):
+    with open(os.path.join(MOJO, name)) as f:
+        return f.read()
+
+
+def test_external_calls_bind_exported_symbols():
+    lib = ctypes.CDLL(b200fft.lib_path())
+    syms = set(re.findall(r'external_call\["(\w+)"', _read("_ffi.mojo")))
+    assert {"b200fft_plan_create", "b200fft_exec", "b200fft_plan_destroy", "b200fft_last_error"} <= syms
+    for s in syms:
+        assert hasattr(lib, s), "the Mojo binding calls %s, which the library does not export" % s
+
+
+def test_descriptor_struct_matches_the_header():
+    header = open(os.path.join(ROOT, "include", "b200fft.h")).read()
+    body = header[header.index("typedef struct b200fft_desc {"):header.index("} b200fft_desc;")]
+    c_fields = re.findall(r"^\s*(?:const\s+)?(\w+)\*?\s+(\w+)(?:\[\w+\])?;", body, flags=re.M)
+    c_names = [n for _, n in c_fields]
+    mojo = _read("_ffi.mojo")
+    sbody = mojo[mojo.index("struct B200Desc"):]
+    sbody = sbody[:sbody.index("\n\n\n")]
+    m_fields = re.findall(r"^\s+var (\w+): ([\w\[\], ]+)$", sbody, flags=re.M)
+    m_names = [n for n, _ in m_fields if not n.startswith("_pad")]
+    assert m_names == c_names, (m_names, c_names)
+    width = {"Int32": 4, "UInt32": 4, "Int64": 8}
+    sizes = []
+    for n, t in m_fields:
+        if t.startswith("InlineArray[Int64"):
+            sizes.append(8 * 8)
+        elif t.startswith("UnsafePointer"):
+            sizes.append(8)
+        else:
+            sizes.append(width[t])
+    assert sum(sizes) == ctypes.sizeof(b200fft._Desc) == 128      # explicit _pad0 after `rank`, no hidden padding
+    # same offsets as the ctypes struct the tests exercise
+    off, offsets = 0, {}
+    for (n, _), sz in zip(m_fields, sizes):
+        offsets[n] = off
+        off += sz
+    for n in c_names:
+        assert offsets[n] == getattr(b200fft._Desc, n).offset, n
+
+
+def test_wrappers_keep_the_reference_entry_points():
+    src = _read("fft.mojo")
+    init = _read("__init__.mojo")
+    assert re.search(r"from \.fft import .*\bfft\b.*\bplan_fft\b", init)
+    plan = src[src.index("def plan_fft["):src.index("def fft[")]
+    for param in ("in_dtype: DType", "out_dtype: DType", "in_layout: Layout", "out_layout: Layout", "bases: List[List[UInt]]",
+                  "inverse: Bool", "runtime_twfs: Bool", "max_cluster_size: UInt", "ctx: DeviceContext"):
+        assert param in plan, param
+    fft = src[src.index("def fft["):src.index("def rfft_half[")]
+    for param in ("output: LayoutTensor[out_dtype, out_layout, out_origin]", "x: LayoutTensor[in_dtype, in_layout, in_origin]",
+                  "ctx: DeviceContext", "plan: B200Plan"):
+        assert param in fft, param
+    assert "_check_layout_conditions_nd[in_layout, out_layout]()" in fft and "raises" in fft
