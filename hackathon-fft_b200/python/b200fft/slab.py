@@ -21,6 +21,11 @@ y = h*Y/G + y_local. Two exchange modes share the same kernels:
              exchange overlaps the butterflies on both sides and there is no barrier at all. Cubic
              volumes (64/128/256/512) only.
 
+`restore(out)` (or `forward(x, natural=True)`) is the optional step AFTER the path: a second
+all-to-all that brings the Y-slab result back to the input's Z-slab distribution [Z/G][Y][X]
+(natural order, what a caller chaining forward -> inverse needs). It is not part of the timed
+transform; it uses one all_to_all_single and one strided copy in every exchange mode.
+
 SlabFFT3D owns the decomposition and exchange logic; an `engine` supplies the three local
 operations (alloc, fft2_scatter, fftz). The product engine is CUDA-only (no CPU fallback);
 tests/test_slab_gloo.py injects a numpy engine to run the same orchestration over gloo.
@@ -180,7 +185,24 @@ class SlabFFT3D:
         w = self.plan.timeout_offset // 4
         return int(sum(int(b.tensor[w:w + 1].view(torch.int32).item()) for b in self._bufs))
 
-    def forward(self, x_local):
+    def restore(self, out_local):
+        """Second exchange: the Y-slab result [Z][Y/G][X] of forward() back to the Z-slab distribution
+        [Z/G][Y][X] of the input. Block g of out_local (z in slab g) goes to rank g; rank g
+        receives (its z planes, y rows of slab h) from every h and interleaves them along y."""
+        Z, Y, X = self.dims
+        if tuple(out_local.shape) != (Z, self.yl, X, 2) or not out_local.is_contiguous():
+            raise b200fft.B200FFTError(2, "restore() takes forward()'s dense [Z][Y/G][X][2] result")
+        got = torch.empty((self.world, self.zl, self.yl, X, 2), dtype=out_local.dtype, device=out_local.device)
+        dist.all_to_all_single(got.view(-1), out_local.view(-1), group=self.group)
+        nat = torch.empty((self.zl, Y, X, 2), dtype=out_local.dtype, device=out_local.device)
+        nat.view(self.zl, self.world, self.yl, X, 2).copy_(got.permute(1, 0, 2, 3, 4))
+        return nat
+
+    def forward(self, x_local, natural=False):
+        out = self._forward(x_local)
+        return self.restore(out) if natural else out
+
+    def _forward(self, x_local):
         if self.exchange == "fused":
             k = self.calls & 1
             self.calls += 1

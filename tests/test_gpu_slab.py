@@ -85,3 +85,48 @@ def test_fused_slab_rejects_unsupported():
         b200fft.SlabPlan(100, 1, 0)            # not a registered cubic size
     with pytest.raises(b200fft.B200FFTError):
         b200fft.SlabPlan(128, 3, 0)            # 128 planes cannot be split over 3 ranks
+
+
+def test_pencil_and_slab_restore_single_rank_nccl():
+    """The product engines behind PencilFFT3D and SlabFFT3D.restore() on one GPU (a 1-rank NCCL group; the block
+    order over 2 and 4 ranks is covered on CPU by tests/test_pencil_gloo.py): X / Y / Z passes through axis-masked
+    plans, pack / exchange / unpack, natural-order output and the forward -> inverse round trip."""
+    import os
+    import socket
+    import torch
+    import torch.distributed as dist
+    from b200fft.pencil import PencilFFT3D
+    from b200fft.slab import SlabFFT3D
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        g = torch.Generator(device="cuda").manual_seed(21)
+        for dims, inverse in (((64, 96, 128), False), ((32, 64, 100), True)):
+            x = torch.randn(dims + (2,), generator=g, device="cuda")
+            keep = x.clone()
+            pen = PencilFFT3D(dims, (1, 1), inverse=inverse)
+            got = torch.view_as_complex(pen.forward(x).double().contiguous())
+            xc = torch.view_as_complex(x.double().contiguous())
+            want = torch.fft.ifftn(xc) if inverse else torch.fft.fftn(xc)
+            assert float((got - want).norm() / want.norm()) < 2e-6
+            assert torch.equal(x, keep)
+            pen.close()
+        dims = (64, 64, 64)
+        x = torch.randn(dims + (2,), generator=g, device="cuda")
+        xc = torch.view_as_complex(x.double().contiguous())
+        for mode in ("nccl", "p2p", "fused"):
+            fwd = SlabFFT3D(dims, exchange=mode)
+            inv = SlabFFT3D(dims, exchange=mode, inverse=True)
+            spec = fwd.forward(x, natural=True)
+            want = torch.fft.fftn(xc)
+            assert float((torch.view_as_complex(spec.double().contiguous()) - want).norm() / want.norm()) < 2e-6
+            back = inv.forward(spec, natural=True)
+            assert float((back - x).norm() / x.norm()) < 2e-6
+            fwd.close()
+            inv.close()
+    finally:
+        dist.destroy_process_group()

@@ -40,6 +40,41 @@ def check(n, mode, rank, world):
     return errs
 
 
+def check_restore_and_pencil(n, rank, world):
+    """Natural-order output (second exchange), forward -> inverse round trip, and the pencil decomposition on the
+    most square grid the world size allows; relative L2 per rank, gathered."""
+    from b200fft.pencil import PencilFFT3D
+    zl = n // world
+    g = torch.Generator(device="cuda").manual_seed(200 + rank)
+    x = torch.randn((zl, n, n, 2), generator=g, device="cuda")
+    full = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(full, x)
+    want = torch.fft.fftn(torch.view_as_complex(torch.cat(full, 0).double().contiguous()))
+    fwd, inv = SlabFFT3D((n, n, n), exchange="p2p"), SlabFFT3D((n, n, n), exchange="p2p", inverse=True)
+    spec = fwd.forward(x, natural=True)
+    e_nat = float((torch.view_as_complex(spec.double().contiguous()) - want[rank * zl:(rank + 1) * zl]).norm()
+                  / want[rank * zl:(rank + 1) * zl].norm())
+    back = inv.forward(spec, natural=True)
+    e_rt = float((back - x).norm() / x.norm())
+    fwd.close()
+    inv.close()
+    P0 = max(d for d in (1, 2, 4, 8) if world % d == 0 and d * d <= world)
+    P1 = world // P0
+    p0, p1 = divmod(rank, P1)
+    vol = torch.cat(full, 0)
+    zp, yp = n // P0, n // P1
+    xl = vol[p0 * zp:(p0 + 1) * zp, p1 * yp:(p1 + 1) * yp].contiguous()
+    pen = PencilFFT3D((n, n, n), (P0, P1))
+    got = torch.view_as_complex(pen.forward(xl).double().contiguous())
+    ref = want[:, p0 * (n // P0):(p0 + 1) * (n // P0), p1 * (n // P1):(p1 + 1) * (n // P1)]
+    e_pen = float((got - ref).norm() / ref.norm())
+    pen.close()
+    errs = [None] * world
+    dist.all_gather_object(errs, (e_nat, e_rt, e_pen))
+    return {"natural_out_max_rel_l2": max(e[0] for e in errs), "round_trip_max_rel_l2": max(e[1] for e in errs),
+            "pencil_grid": [P0, P1], "pencil_max_rel_l2": max(e[2] for e in errs)}
+
+
 def bench(n, mode, rank, world, steps, warmup):
     zl = n // world
     x = torch.randn((zl, n, n, 2), device="cuda")
@@ -81,6 +116,10 @@ def main():
             res["ms_%d_%s" % (a.n, mode)] = bench(a.n, mode, rank, world, a.steps, a.warmup)
         except Exception as e:  # report, keep going with the other modes
             res["error_" + mode] = "%s: %s" % (type(e).__name__, e)
+    try:
+        res["check128_restore_pencil"] = check_restore_and_pencil(128, rank, world)
+    except Exception as e:
+        res["error_restore_pencil"] = "%s: %s" % (type(e).__name__, e)
     for d in [v for v in a.delays.split(",") if v]:
         os.environ["B200FFT_SLAB_DELAY"] = d
         try:
