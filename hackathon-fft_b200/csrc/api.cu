@@ -40,6 +40,7 @@ int upload_twiddles(int64_t n, bool inverse, bool f64, DeviceTwiddles* out) {
       h[(size_t)k] = make_double2(std::cos(th), sgn * std::sin(th));
     }
     B200_CUDA_CHECK(cudaMalloc(&d, sizeof(double2) * (size_t)n));
+    out->ptr = d;  // owned by the plan from here on: a failed copy is freed by b200fft_plan_destroy
     B200_CUDA_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice));
   } else {
     std::vector<float2> h((size_t)n);
@@ -48,6 +49,7 @@ int upload_twiddles(int64_t n, bool inverse, bool f64, DeviceTwiddles* out) {
       h[(size_t)k] = make_float2((float)std::cos(th), (float)(sgn * std::sin(th)));
     }
     B200_CUDA_CHECK(cudaMalloc(&d, sizeof(float2) * (size_t)n));
+    out->ptr = d;
     B200_CUDA_CHECK(cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice));
   }
   out->ptr = d;
@@ -279,7 +281,10 @@ int b200fft_plan_create(b200fft_plan** out, const b200fft_desc* desc) {
   if (rc != B200FFT_OK) { b200fft_plan_destroy(plan.release()); return rc; }
   // The tables were uploaded with cudaMemcpy from pageable memory on the legacy stream: make sure they have landed
   // before the caller launches on a non-blocking stream of its own (which is not ordered after the legacy stream).
-  B200_CUDA_CHECK(cudaDeviceSynchronize());
+  if (cudaError_t e = cudaDeviceSynchronize(); e != cudaSuccess) {
+    b200fft_plan_destroy(plan.release());
+    return fail(B200FFT_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
+  }
   *out = plan.release();
   return B200FFT_OK;
 }
@@ -403,38 +408,48 @@ int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in) {
     int64_t chunk = std::max<int64_t>(1, (p.batch + nchunks - 1) / nchunks);
     if (plan->chunk_batches > 0) chunk = ((chunk + plan->chunk_batches - 1) / plan->chunk_batches) * plan->chunk_batches;
     plan->host_chunk = chunk;
-    for (int i = 0; i < 3; ++i) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->hs[i], cudaStreamNonBlocking));
+    // each resource is created only while still null, so a call that failed half way through can be retried
+    // without leaking what it had already made (b200fft_plan_destroy frees whatever exists)
+    for (int i = 0; i < 3; ++i)
+      if (!plan->hs[i]) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->hs[i], cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-      B200_CUDA_CHECK(cudaMalloc(&plan->h_dev_in[i], (size_t)chunk * in_stride));
-      B200_CUDA_CHECK(cudaMalloc(&plan->h_dev_out[i], (size_t)chunk * out_stride));
+      if (!plan->h_dev_in[i]) B200_CUDA_CHECK(cudaMalloc(&plan->h_dev_in[i], (size_t)chunk * in_stride));
+      if (!plan->h_dev_out[i]) B200_CUDA_CHECK(cudaMalloc(&plan->h_dev_out[i], (size_t)chunk * out_stride));
     }
-    for (auto& e : plan->h_ev) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : plan->h_ev)
+      if (!e) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     plan->host_ready = true;
   }
   cudaEvent_t* ev_in = &plan->h_ev[0];    // [2] H2D done
   cudaEvent_t* ev_k = &plan->h_ev[2];     // [2] kernels done
   cudaEvent_t* ev_out = &plan->h_ev[4];   // [2] D2H done
   const int64_t chunk = plan->host_chunk;
-  int64_t k = 0;
-  for (int64_t b0 = 0; b0 < p.batch; b0 += chunk, ++k) {
-    const int slot = (int)(k & 1);
-    const int64_t nb = std::min<int64_t>(chunk, p.batch - b0);
-    if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[0], ev_k[slot], 0));  // input slot consumed
-    B200_CUDA_CHECK(cudaMemcpyAsync(plan->h_dev_in[slot], (const char*)h_in + (size_t)b0 * in_stride,
-                                    (size_t)nb * in_stride, cudaMemcpyHostToDevice, plan->hs[0]));
-    B200_CUDA_CHECK(cudaEventRecord(ev_in[slot], plan->hs[0]));
-    B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[1], ev_in[slot], 0));
-    if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[1], ev_out[slot], 0));  // output slot drained
-    int rc = run_passes(plan, plan->h_dev_out[slot], plan->h_dev_in[slot], nb, plan->hs[1], b0);
-    if (rc != B200FFT_OK) return rc;
-    B200_CUDA_CHECK(cudaEventRecord(ev_k[slot], plan->hs[1]));
-    B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[2], ev_k[slot], 0));
-    B200_CUDA_CHECK(cudaMemcpyAsync((char*)h_out + (size_t)b0 * out_stride, plan->h_dev_out[slot],
-                                    (size_t)nb * out_stride, cudaMemcpyDeviceToHost, plan->hs[2]));
-    B200_CUDA_CHECK(cudaEventRecord(ev_out[slot], plan->hs[2]));
-  }
-  B200_CUDA_CHECK(cudaStreamSynchronize(plan->hs[2]));
-  return B200FFT_OK;
+  auto pipeline = [&]() -> int {
+    int64_t k = 0;
+    for (int64_t b0 = 0; b0 < p.batch; b0 += chunk, ++k) {
+      const int slot = (int)(k & 1);
+      const int64_t nb = std::min<int64_t>(chunk, p.batch - b0);
+      if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[0], ev_k[slot], 0));  // input slot consumed
+      B200_CUDA_CHECK(cudaMemcpyAsync(plan->h_dev_in[slot], (const char*)h_in + (size_t)b0 * in_stride,
+                                      (size_t)nb * in_stride, cudaMemcpyHostToDevice, plan->hs[0]));
+      B200_CUDA_CHECK(cudaEventRecord(ev_in[slot], plan->hs[0]));
+      B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[1], ev_in[slot], 0));
+      if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[1], ev_out[slot], 0));  // output slot drained
+      int rc = run_passes(plan, plan->h_dev_out[slot], plan->h_dev_in[slot], nb, plan->hs[1], b0);
+      if (rc != B200FFT_OK) return rc;
+      B200_CUDA_CHECK(cudaEventRecord(ev_k[slot], plan->hs[1]));
+      B200_CUDA_CHECK(cudaStreamWaitEvent(plan->hs[2], ev_k[slot], 0));
+      B200_CUDA_CHECK(cudaMemcpyAsync((char*)h_out + (size_t)b0 * out_stride, plan->h_dev_out[slot],
+                                      (size_t)nb * out_stride, cudaMemcpyDeviceToHost, plan->hs[2]));
+      B200_CUDA_CHECK(cudaEventRecord(ev_out[slot], plan->hs[2]));
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(plan->hs[2]));
+    return B200FFT_OK;
+  };
+  const int rc = pipeline();
+  if (rc != B200FFT_OK)  // the caller may free its host buffers once we return: no copy may still be in flight
+    for (int i = 0; i < 3; ++i) cudaStreamSynchronize(plan->hs[i]);
+  return rc;
 }
 
 size_t b200fft_plan_workspace_bytes(const b200fft_plan* plan) { return plan ? plan->workspace_bytes : 0; }
