@@ -53,6 +53,13 @@ SHAPES = [
     ("3d_10x128x128x128", (10, 128, 128, 128), False),
     ("3d_1x256x256x256", (1, 256, 256, 256), False),
     ("3d_1x512x512x512", (1, 512, 512, 512), False),
+    # half-spectrum R2C of the 1-D and 3-D configs (what cufft_benchmark.cu's R2C rows time, :34-46)
+    ("1d_500000x128_r2c_half", (500000, 128), "half"),
+    ("1d_100000x1024_r2c_half", (100000, 1024), "half"),
+    ("1d_500000x93_r2c_half", (500000, 93), "half"),
+    ("3d_100x64x64x64_r2c_half", (100, 64, 64, 64), "half"),
+    ("3d_10x128x128x128_r2c_half", (10, 128, 128, 128), "half"),
+    ("3d_1x256x256x256_r2c_half", (1, 256, 256, 256), "half"),
 ]
 
 

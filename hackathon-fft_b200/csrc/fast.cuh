@@ -132,6 +132,12 @@ struct is_pairwise : std::false_type {};
 template <class T>
 struct is_pairwise<T, std::enable_if_t<T::pairwise>> : std::true_type {};
 
+// destinations that take a butterfly's R outputs at once (register-level epilogues, e.g. R2CRegDst)
+template <class T, class = void>
+struct is_whole : std::false_type {};
+template <class T>
+struct is_whole<T, std::enable_if_t<T::whole>> : std::true_type {};
+
 template <class Layout>
 struct SmemSrc {
   const float2* buf;
@@ -215,7 +221,10 @@ __device__ __forceinline__ void run_stage(const Src& src, const Dst& dst, const 
 #pragma unroll
         for (int k = 0; k < R; ++k) { x[k].x *= scale; x[k].y *= scale; }
       }
-      if constexpr (is_pairwise<Dst>::value) {
+      if constexpr (is_whole<Dst>::value) {
+        static_assert(CN == 1 && TOTAL % 32 == 0 && NT % 32 == 0, "whole-butterfly stores: rows, warp-uniform activity");
+        dst.template store_all<R, P>(o, g, p, x);
+      } else if constexpr (is_pairwise<Dst>::value) {
         static_assert(CN == 1 && P % 2 == 0 && R % 2 == 0 && NT % 2 == 0, "pairwise stores: even P, R, NT");
         const bool odd = (threadIdx.x & 1) != 0;
         const unsigned mask = __activemask();
@@ -457,6 +466,90 @@ __global__ void __launch_bounds__(NT) rows_r2c_kernel(const __grid_constant__ Ha
   const int valid = (int)min((long long)C, a.nrows - row0);
   r2c_tile<H, RL, C, NT>(reinterpret_cast<const float2*>(a.in) + row0 * H,
                          reinterpret_cast<float2*>(a.out) + row0 * (H + 1), a.tw, a.tw2, valid, smem_f2);
+}
+
+// ---- R2C with the Hermitian unpack in registers (warp shuffles instead of a shared-memory pass) ----------
+// In the LAST stage (radix R, P = H / R butterflies per row) the thread of butterfly p holds
+// Z[p + k*P], k = 0..R-1. The mirrored bins it needs are H - (p + k*P) = (P - p) + (R-1-k)*P: exactly the
+// outputs of butterfly P - p of the same row, in reverse order (butterfly 0 mirrors onto itself,
+// Z[H - k*P] = its own output R - k, and Z[H] = Z[0]). When P divides 32 the butterflies of a row sit in
+// consecutive lanes of one warp, so the partner's value arrives with one __shfl_sync per component and the
+// unpacked bins go straight from registers to global memory: no Z buffer, no extra barrier, and the kernel
+// needs only the exchange buffer(s) of the H-point transform (none at all for a single-stage H).
+template <int H>
+struct R2CRegDst {
+  static constexpr bool whole = true;
+  float2* __restrict__ out;          // first output row of the tile; rows of H + 1 bins
+  const float2* __restrict__ tw2;    // W_n^k, k = 0..H
+  int valid_o;
+  template <int R, int P>
+  __device__ __forceinline__ void store_all(int o, int g, int p, const float2 (&x)[R]) const {
+    static_assert(P * R == H && P <= 32 && 32 % P == 0, "last stage of an H-point transform, rows inside a warp");
+    (void)g;  // always 0 in the last stage
+    const int lane = (int)threadIdx.x & 31;
+    const int partner = (lane & ~(P - 1)) | ((P - p) & (P - 1));
+    float2* __restrict__ row = out + (long long)o * (H + 1);
+    const bool live = o < valid_o;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      float2 zm = x[(R - k) % R];  // butterfly 0: its own mirrored output
+      if constexpr (P > 1) {
+        const float mx = __shfl_sync(0xffffffffu, x[R - 1 - k].x, partner);
+        const float my = __shfl_sync(0xffffffffu, x[R - 1 - k].y, partner);
+        if (p != 0) zm = make_float2(mx, my);
+      }
+      const float2 zk = x[k];
+      // s = Z[k] + conj(Z[H-k]), d = Z[k] - conj(Z[H-k])
+      const float2 s = make_float2(zk.x + zm.x, zk.y - zm.y), d = make_float2(zk.x - zm.x, zk.y + zm.y);
+      const float2 t = cmulf(d, __ldg(&tw2[p + k * P]));
+      if (live) row[p + k * P] = make_float2(0.5f * (s.x + t.y), 0.5f * (s.y - t.x));  // (s - i t) / 2
+    }
+    if (p == 0 && live) row[H] = make_float2(x[0].x - x[0].y, 0.f);  // X[H] = Re Z[0] - Im Z[0]
+  }
+};
+template <int H, class RL, int C, int NT>
+constexpr bool r2c_reg_ok() {
+  constexpr int P = H / RL::r[RL::count - 1];
+  // P >= 8: a warp's store covers segments of P consecutive bins; with fewer (single-stage H: P = 1, every lane a
+  // different row) the stores are uncoalesced and the shared-memory unpack wins (measured: 100 x 64^3 R2C 0.172 vs 0.208 ms)
+  return P >= 8 && P <= 32 && 32 % P == 0 && (C * P) % 32 == 0 && NT % 32 == 0;
+}
+template <int H, class RL, int C>
+constexpr size_t rows_r2c_reg_smem_bytes() {
+  return sizeof(float2) * (size_t)max_exchange_elems<RL, C, RowLayoutN<H>::template type>() * (RL::count > 2 ? 2 : 1);
+}
+template <int H, class RL, int C, int NT>
+__global__ void __launch_bounds__(NT) rows_r2c_reg_kernel(const __grid_constant__ HalfArgs a) {
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
+  const long long row0 = (long long)blockIdx.x * C;
+  const int valid = (int)min((long long)C, a.nrows - row0);
+  GlobalSrc<false> src{reinterpret_cast<const float2*>(a.in) + row0 * H, H, 1, valid, 1};
+  R2CRegDst<H> dst{reinterpret_cast<float2*>(a.out) + row0 * (H + 1), a.tw2, valid};
+  run_axis<RL, H, C, 1, NT, false, RowLayoutN<H>::template type>(src, dst, smem_f2, smem_f2 + EX, a.tw, 1.f, false);
+}
+
+// ---- R2C of an ODD length n: the n-point transform of the real row on the row kernel's stages, storing only
+// bins 0..n/2 (rows of n/2 + 1 bins). One read of 4 B and one write of ~4 B per input point.
+struct GlobalHalfDst {
+  float2* __restrict__ base;
+  int bins;  // n/2 + 1 = output row stride
+  int valid_o;
+  __device__ __forceinline__ void store(int o, int i, int, float2 v) const {
+    if (o >= valid_o || i >= bins) return;
+    base[(long long)o * bins + i] = v;
+  }
+};
+template <int N, class RL, int C, int NT>
+__global__ void __launch_bounds__(NT) rows_r2c_odd_kernel(const __grid_constant__ HalfArgs a) {
+  static_assert(N % 2 == 1, "odd lengths only (even lengths run as an n/2-point complex transform)");
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
+  const long long row0 = (long long)blockIdx.x * C;
+  const int valid = (int)min((long long)C, a.nrows - row0);
+  GlobalSrc<true> src{reinterpret_cast<const float*>(a.in) + row0 * N, N, 1, valid, 1};
+  GlobalHalfDst dst{reinterpret_cast<float2*>(a.out) + row0 * (N / 2 + 1), N / 2 + 1, valid};
+  run_axis<RL, N, C, 1, NT, false, RowLayoutN<N>::template type>(src, dst, smem_f2, smem_f2 + BUF, a.tw, 1.f, false);
 }
 
 // stage-0 source of the C2R kernel: Z[k] from the staged half spectrum

@@ -22,6 +22,7 @@ void register_rows_pow2() {
   reg_rows<512, 8, 256, true, 32, 16>();
   reg_rows_v4<512, 8, 256, true, 32, 16>();
   reg_rows<512, 8, 256, true, 8, 8, 8>();
+  reg_rows<512, 16, 256, true, 32, 16>();  // 16 rows: every thread busy in the radix-32 stage (R2C of 1024-point rows)
   reg_rows<1024, 8, 256, true, 32, 32>();
   reg_rows_v4<1024, 8, 256, true, 32, 32>();
   reg_rows<1024, 4, 256, true, 16, 16, 4>();

@@ -157,6 +157,7 @@ namespace {
 struct FastPass : Pass {
   const Variant* v = nullptr;
   HalfMode half = HALF_NONE;
+  enum R2CMode { R2C_SMEM = 0, R2C_REG = 1, R2C_ODD = 2 } r2c_mode = R2C_SMEM;  // which R2C kernel (fast.cuh)
   float2* d_tw2 = nullptr;
   AxisView view;
   bool inverse = false, real_in = false, do_scale = false;
@@ -176,7 +177,9 @@ struct FastPass : Pass {
       const long long grid = (a.nrows + v->tile - 1) / v->tile;
       if (grid <= 0) return B200FFT_OK;
       if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many row tiles");
-      v->launch_half(half == HALF_C2R, a, (unsigned)grid, stream);
+      if (half == HALF_R2C && r2c_mode == R2C_REG) v->launch_r2c_reg(a, (unsigned)grid, stream);
+      else if (half == HALF_R2C && r2c_mode == R2C_ODD) v->launch_r2c_odd(a, (unsigned)grid, v->smem, stream);
+      else v->launch_half(half == HALF_C2R, a, (unsigned)grid, stream);
     } else if (v->kind == ROWS) {
       RowsArgs a;
       a.in = src;
@@ -263,7 +266,12 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   const AxisSpec& ax = p.axes[axis];
 
   std::vector<const Variant*> cands;
-  if (half != HALF_NONE) {
+  const bool odd_r2c = half == HALF_R2C && kind == ROWS && view.n % 2 == 1;
+  if (odd_r2c) {
+    // odd n: the n-point row variant itself on real input, storing bins 0..n/2 (C2R of odd n stays on the rt tier)
+    for (const Variant& v : registry())
+      if (v.kind == ROWS && v.n == (int)view.n && v.launch_r2c_odd && can_group(ax.ordered, v.radices)) cands.push_back(&v);
+  } else if (half != HALF_NONE) {
     if (kind != ROWS || view.n % 2) return nullptr;
     const auto reduced = drop_factor_two(ax.ordered);
     for (const Variant& v : registry()) {
@@ -310,7 +318,12 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
     });
   }
   const Variant* v = cands[0];
-  if ((half != HALF_NONE ? v->prepare_half() : v->prepare(v->smem)) != cudaSuccess) {
+  // B200FFT_R2C_SMEM=1: keep the shared-memory Hermitian unpack (A/B knob for the register unpack)
+  const char* r2c_env = getenv("B200FFT_R2C_SMEM");
+  const bool r2c_reg = half == HALF_R2C && !odd_r2c && v->launch_r2c_reg && !(r2c_env && atoi(r2c_env) != 0);
+  cudaError_t prep = odd_r2c ? v->prepare_r2c_odd(v->smem) : half != HALF_NONE ? v->prepare_half() : v->prepare(v->smem);
+  if (prep == cudaSuccess && r2c_reg) prep = v->prepare_r2c_reg();
+  if (prep != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
@@ -322,7 +335,9 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   pass->do_scale = scale_inverse;
   pass->scale = scale_inverse ? (float)(1.0 / (double)view.n) : 1.f;
   pass->half = half;
-  if (half != HALF_NONE) {
+  pass->r2c_mode = odd_r2c ? FastPass::R2C_ODD : r2c_reg ? FastPass::R2C_REG : FastPass::R2C_SMEM;
+  if (odd_r2c) pass->real_in = true;
+  if (half != HALF_NONE && !odd_r2c) {
     if (half == HALF_C2R) pass->scale = (float)(1.0 / (double)view.n);  // 1/(2H): the inverse is always normalised
     std::vector<float2> tw2 = build_half_twiddles(view.n, half == HALF_C2R);
     if (cudaMalloc(&pass->d_tw2, tw2.size() * sizeof(float2)) != cudaSuccess) return nullptr;
@@ -336,10 +351,14 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   std::string stages;
   for (uint32_t r : ax.ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
   char buf[320];
-  if (half != HALF_NONE)
+  if (odd_r2c)
+    snprintf(buf, sizeof buf, "axis %d: r2c-odd[%s] n=%lld (real rows, bins 0..n/2 stored) smem=%zuB user stages=[%s] fused as (%s)",
+             axis, v->name.c_str(), (long long)view.n, v->smem, stages.c_str(), radix_name(v->radices).c_str());
+  else if (half != HALF_NONE)
     snprintf(buf, sizeof buf, "axis %d: %s[%s] n=%lld (as %d complex) smem=%zuB user stages=[%s] fused as (2)(%s)", axis,
-             half == HALF_R2C ? "r2c" : "c2r", v->name.c_str(), (long long)view.n, v->n,
-             half == HALF_R2C ? v->smem_r2c : v->smem_c2r, stages.c_str(), radix_name(v->radices).c_str());
+             half == HALF_R2C ? (r2c_reg ? "r2c-reg" : "r2c") : "c2r", v->name.c_str(), (long long)view.n, v->n,
+             half == HALF_R2C ? (r2c_reg ? v->smem_r2c_reg : v->smem_r2c) : v->smem_c2r, stages.c_str(),
+             radix_name(v->radices).c_str());
   else
     snprintf(buf, sizeof buf, "axis %d: %s n=%lld inner=%lld smem=%zuB user stages=[%s] fused as (%s)%s", axis,
              v->name.c_str(), (long long)view.n, (long long)view.inner, v->smem, stages.c_str(),

@@ -31,6 +31,13 @@ struct Variant {
   void (*launch_half)(bool c2r, const HalfArgs&, unsigned, cudaStream_t) = nullptr;
   cudaError_t (*prepare_half)() = nullptr;
   size_t smem_r2c = 0, smem_c2r = 0;
+  // R2C with the Hermitian unpack in registers (fast.cuh, R2CRegDst): when the last stage keeps a row inside a warp
+  void (*launch_r2c_reg)(const HalfArgs&, unsigned, cudaStream_t) = nullptr;
+  cudaError_t (*prepare_r2c_reg)() = nullptr;
+  size_t smem_r2c_reg = 0;
+  // odd n: half-spectrum R2C of length n itself (real rows in, bins 0..n/2 out) on this n-point variant
+  void (*launch_r2c_odd)(const HalfArgs&, unsigned, size_t, cudaStream_t) = nullptr;
+  cudaError_t (*prepare_r2c_odd)(size_t) = nullptr;
 };
 
 std::vector<Variant>& registry();
@@ -84,6 +91,28 @@ struct HalfV {
     cudaError_t e = cudaFuncSetAttribute(rows_r2c_kernel<H, RL, C, NT>, attr, (int)rows_r2c_smem_bytes<H, RL, C>());
     if (!e) e = cudaFuncSetAttribute(rows_c2r_kernel<H, RL, C, NT>, attr, (int)rows_c2r_smem_bytes<H, RL, C>());
     return e;
+  }
+};
+
+template <int H, class RL, int C, int NT>
+struct HalfRegV {
+  static void launch(const HalfArgs& a, unsigned grid, cudaStream_t st) {
+    rows_r2c_reg_kernel<H, RL, C, NT><<<grid, NT, rows_r2c_reg_smem_bytes<H, RL, C>(), st>>>(a);
+  }
+  static cudaError_t prepare() {
+    if (rows_r2c_reg_smem_bytes<H, RL, C>() <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(rows_r2c_reg_kernel<H, RL, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)rows_r2c_reg_smem_bytes<H, RL, C>());
+  }
+};
+template <int N, class RL, int C, int NT>
+struct HalfOddV {
+  static void launch(const HalfArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    rows_r2c_odd_kernel<N, RL, C, NT><<<grid, NT, smem, st>>>(a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(rows_r2c_odd_kernel<N, RL, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
 };
 
@@ -167,6 +196,15 @@ void reg_rows_impl() {
     if (v.smem_r2c <= 227 * 1024 && v.smem_c2r <= 227 * 1024) {
       v.launch_half = &HalfV<N, RL, C, NT>::launch;
       v.prepare_half = &HalfV<N, RL, C, NT>::prepare;
+      if constexpr (r2c_reg_ok<N, RL, C, NT>()) {
+        v.launch_r2c_reg = &HalfRegV<N, RL, C, NT>::launch;
+        v.prepare_r2c_reg = &HalfRegV<N, RL, C, NT>::prepare;
+        v.smem_r2c_reg = rows_r2c_reg_smem_bytes<N, RL, C>();
+      }
+    }
+    if constexpr (N % 2 == 1) {
+      v.launch_r2c_odd = &HalfOddV<N, RL, C, NT>::launch;
+      v.prepare_r2c_odd = &HalfOddV<N, RL, C, NT>::prepare;
     }
   }
   v.full = FULL;

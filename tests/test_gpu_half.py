@@ -87,7 +87,7 @@ def test_fast_path_is_used_for_the_benchmark_shape():
     rng = np.random.default_rng(0)
     x = rng.standard_normal((2, 640, 480, 1)).astype(np.float32)
     _, desc = r2c(x)
-    assert "r2c[rows240" in desc and "cols640" in desc, desc
+    assert "r2c" in desc and "[rows240" in desc and "cols640" in desc, desc
 
 
 def test_half_matches_reference_full_mode():
@@ -138,13 +138,15 @@ def test_f64_and_errors():
 
 
 def test_unregistered_lengths_use_the_rt_tier():
-    """Half-spectrum rows without a fused R2C/C2R kernel (odd or unregistered lengths) run on the runtime-length
-    tier (n-point transform, bins 0..n/2 stored / Hermitian-extended load), not on the generic kernel."""
+    """Half-spectrum rows without a fused R2C/C2R kernel run on the runtime-length tier (n-point transform, bins
+    0..n/2 stored / Hermitian-extended load), not on the generic kernel; an odd length with a registered row variant
+    (93 = 31 x 3) runs its R2C on that compile-time kernel with a half-bins store (C2R of odd n stays on the rt tier)."""
     rng = np.random.default_rng(4)
-    for shape in ((6, 93), (3, 1000), (2, 12, 30)):
+    for shape, kernel in (((6, 93), "r2c-odd[rows93"), ((3, 1000), "rt_rows"), ((2, 12, 30), "rt_rows"),
+                          ((2, 20, 93), "r2c-odd[rows93")):
         x = rng.standard_normal(shape + (1,)).astype(np.float32)
         got, desc = r2c(x)
-        assert "rt_rows" in desc and "generic" not in desc, desc
+        assert kernel in desc and "generic" not in desc, desc
         want = np.fft.rfftn(x[..., 0].astype(np.float64), axes=tuple(range(1, len(shape))))
         assert np.linalg.norm(c2(got) - want) <= 2e-6 * np.sqrt(len(shape) - 1) * np.linalg.norm(want)
         back, _ = c2r(got, shape[-1])
