@@ -11,6 +11,9 @@ void register_cols_pow2() {
   reg_cols<512, 8, 128, false, 32, 16>();
   reg_cols<512, 16, 512, false, 32, 16>();
   reg_cols<1024, 8, 256, true, 32, 32>();
+  // Tried and dropped: a 33-column tile for the middle pass of a 64^3 R2C (inner = 33 = the half spectrum of a 64-point real
+  // axis, one contiguous 16.9 KB block per tile instead of 2 full 16-column tiles + 1 column): 100 x 64^3 R2C 0.1727 ms vs
+  // 0.1717 ms with the 16-column tiles (profiles/r1_r2c.md) - the ragged tile is not what bounds that shape.
   // Tried and dropped: single-stage register columns (one thread = one strided 64-point transform, radix-64
   // codelet, 154 registers, no shared memory, no barrier; 17 instructions per point instead of 35):
   // 100 x 64^3 0.2099 ms vs 0.1972 ms with the two-stage 8x8 tiles, 64^4 0.1810 vs 0.1673 ms (gpurun_out/sweep_r64.log).
