@@ -134,3 +134,28 @@ def test_header_is_plain_c_and_links(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                            str(src), "-o", str(exe), "-L", libdir, "-lb200fft", "-Wl,-rpath," + libdir])
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+@pytest.mark.parametrize("H,R", [(512, 16), (64, 8), (128, 8), (256, 16), (240, 15), (160, 10), (48, 3), (640, 20), (1024, 32)])
+def test_r2c_register_unpack_index_algebra(H, R):
+    """The lane algebra behind R2CRegDst (csrc/fast.cuh), restated in numpy: in the last stage of an H-point transform
+    (radix R, P = H / R butterflies per row) butterfly p holds Z[p + k P]; the mirrored bins Z[H - p - k P] are
+    butterfly (P - p) mod P's outputs R-1-k (butterfly 0: its own outputs (R - k) mod R), and
+    X[k] = ((Z[k] + conj Z[H-k]) - i W_n^k (Z[k] - conj Z[H-k])) / 2, X[H] = Re Z[0] - Im Z[0], is the real transform."""
+    P = H // R
+    assert P * R == H and 8 <= P <= 32 and 32 % P == 0          # the eligibility rule r2c_reg_ok() applies
+    rng = np.random.default_rng(H)
+    x = rng.standard_normal(2 * H)
+    Z = np.fft.fft(x[0::2] + 1j * x[1::2])
+    held = np.array([[Z[p + k * P] for k in range(R)] for p in range(P)])     # held[p][k]: registers of butterfly p
+    X = np.empty(H + 1, dtype=complex)
+    for p in range(P):
+        partner = (P - p) % P
+        for k in range(R):
+            zm = held[p][(R - k) % R] if p == 0 else held[partner][R - 1 - k]
+            assert zm == Z[(H - (p + k * P)) % H]
+            zk = held[p][k]
+            s, d = zk + np.conj(zm), zk - np.conj(zm)
+            X[p + k * P] = 0.5 * (s - 1j * np.exp(-2j * np.pi * (p + k * P) / (2 * H)) * d)
+    X[H] = Z[0].real - Z[0].imag
+    np.testing.assert_allclose(X, np.fft.rfft(x), atol=1e-10)
