@@ -159,3 +159,51 @@ def test_r2c_register_unpack_index_algebra(H, R):
             X[p + k * P] = 0.5 * (s - 1j * np.exp(-2j * np.pi * (p + k * P) / (2 * H)) * d)
     X[H] = Z[0].real - Z[0].imag
     np.testing.assert_allclose(X, np.fft.rfft(x), atol=1e-10)
+
+
+def test_cpp_host_layer_mirrors_the_reference_api(tmp_path):
+    """include/b200fft.hpp: the header-only C++ host layer (plan_fft / fft with the reference's names over the C ABI).
+    Compile a C++17 program against it with -Wall -Wextra -Werror, link the built library and exercise everything
+    that needs no GPU: base rules, dry run, the layout / bases errors with the C ABI's status codes, and the loud
+    failure of plan_fft without an sm_100 device (no CPU fallback)."""
+    import subprocess
+    src = tmp_path / "host.cpp"
+    src.write_text(r'''
+#include "b200fft.hpp"
+#include <cstdio>
+#include <cstring>
+int main() {
+  using namespace b200fft;
+  if (ordered_bases(60, {5, 3, 2}) != std::vector<uint32_t>({5, 3, 2, 2})) return 1;   // _utils.mojo:163-183
+  if (!ordered_bases(60, {7}).empty()) return 2;                                       // rejected like the reference
+  if (default_bases(93) != std::vector<uint32_t>({31, 3})) return 3;                   // fft.mojo:49-104
+  Layout img{{100, 640, 480, 2}};
+  PlanOptions o;
+  o.bases = {{5, 2}, {5, 3, 2}};
+  const std::string txt = dry_run(f32, f32, img, img, o);
+  if (txt.find("stages=[5,2,2,2,2,2,2,2]") == std::string::npos || txt.find("stages=[5,3,2,2,2,2,2]") == std::string::npos) return 4;
+  try { dry_run(f32, f32, Layout{{8, 2}}, Layout{{8, 2}}); return 5; } catch (const Error& e) { if (e.status() != B200FFT_ERR_LAYOUT) return 6; }
+  try { o.bases = {{7}, {5, 3, 2}}; dry_run(f32, f32, img, img, o); return 7; } catch (const Error& e) { if (e.status() != B200FFT_ERR_BASES) return 8; }
+  try { o.bases = {{5, 2}}; dry_run(f32, f32, img, img, o); return 9; } catch (const Error& e) { if (e.status() != B200FFT_ERR_BASES) return 10; }
+  PlanOptions h;
+  h.real_mode = real_half;
+  const std::string half = dry_run(f32, f32, Layout{{100, 640, 480, 1}}, Layout{{100, 640, 241, 2}}, h);
+  if (half.find("r2c") == std::string::npos) return 11;
+  try { dry_run(f32, f32, Layout{{100, 640, 480, 1}}, Layout{{100, 640, 240, 2}}, h); return 12; } catch (const Error& e) { if (e.status() != B200FFT_ERR_LAYOUT) return 13; }
+  try {
+    Plan p = plan_fft(f32, f32, Layout{{4, 128, 2}}, Layout{{4, 128, 2}});
+    Plan q = std::move(p);                       // move-only handle
+    if (p || !q || q.launches() < 1) return 14;  // a GPU box: the plan exists and describes its kernels
+  } catch (const Error& e) {
+    if (e.status() != B200FFT_ERR_CUDA) return 15;   // no sm_100 device: loud failure, never a CPU path
+    std::printf("no-gpu: %s\n", e.what());
+  }
+  return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(b200fft.lib_path())
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lb200fft", "-Wl,-rpath," + libdir])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
