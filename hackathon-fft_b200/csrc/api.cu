@@ -188,6 +188,15 @@ int b200fft_version(void) { return 100; }
 
 uint64_t b200fft_launch_count(void) { return g_launch_count.load(); }
 
+int b200fft_variant_count(int tier) {
+  switch (tier) {
+    case 0: return (int)fast_variant_count();
+    case 1: return (int)fused_variant_count();
+    case 2: return (int)split_variant_count();
+    default: return -1;
+  }
+}
+
 const char* b200fft_last_error(void) { return last_error().c_str(); }
 
 const char* b200fft_strerror(int status) {

@@ -36,14 +36,17 @@ void register_cols_tma();
 namespace {
 
 void register_all() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  register_rows_pow2();
-  register_rows_mixed();
-  register_cols_pow2();
-  register_cols_mixed();
-  register_cols_tma();
+  // function-local static: initialised exactly once even when two threads create their first plans concurrently
+  // (include/b200fft.h promises that distinct plans may be used from distinct threads)
+  static const bool done = [] {
+    register_rows_pow2();
+    register_rows_mixed();
+    register_cols_pow2();
+    register_cols_mixed();
+    register_cols_tma();
+    return true;
+  }();
+  (void)done;
 }
 
 }  // namespace
@@ -255,6 +258,11 @@ struct FastPass : Pass {
 };
 
 }  // namespace
+
+size_t fast_variant_count() {
+  register_all();
+  return registry().size();
+}
 
 std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
                                      bool scale_inverse, HalfMode half) {

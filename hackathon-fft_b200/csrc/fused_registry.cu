@@ -38,13 +38,14 @@ void register_fused_async_2d();
 namespace {
 
 void register_all_fused() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  register_fused_async_3d();  // v2 first: preferred when applicable
-  register_fused_async_2d();
-  register_fused_3d();
-  register_fused_2d();
+  static const bool done = [] {  // thread-safe one-time initialisation (see register_all, fast_registry.cu)
+    register_fused_async_3d();  // v2 first: preferred when applicable
+    register_fused_async_2d();
+    register_fused_3d();
+    register_fused_2d();
+    return true;
+  }();
+  (void)done;
 }
 
 // Two persistent kernels with STATIC work assignment (fused2.cuh) must not share the SMs: each sizes its grid
@@ -168,6 +169,11 @@ struct FusedPass : Pass {
 };
 
 }  // namespace
+
+size_t fused_variant_count() {
+  register_all_fused();
+  return fused_registry().size();
+}
 
 std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
   register_all_fused();

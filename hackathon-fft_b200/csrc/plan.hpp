@@ -99,5 +99,9 @@ std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView&
                                    bool scale_inverse, HalfMode half = HALF_NONE);
 // fused N-d kernel (fused_registry.cu): one pass object that replaces ALL per-axis passes, or nullptr
 std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan);
+// number of registered kernel variants per tier (host-only; triggers the one-time registration)
+size_t fast_variant_count();
+size_t fused_variant_count();
+size_t split_variant_count();
 
 }  // namespace b200fft

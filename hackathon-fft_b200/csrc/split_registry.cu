@@ -22,22 +22,23 @@ std::vector<SplitKernel>& split_registry() {
 namespace {
 
 void register_split() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  // pass A candidates (N1): <role, N, columns per tile, threads, super-stages...>
-  reg_split<SPLIT_A, 128, 16, 128, 16, 8>();
-  reg_split<SPLIT_A, 256, 16, 256, 16, 16>();
-  reg_split<SPLIT_A, 512, 16, 256, 32, 16>();
-  reg_split<SPLIT_A, 512, 16, 256, 8, 8, 8>();  // the reference's default bases for 7680 are [15, 8, 8, 8]
-  reg_split<SPLIT_A, 64, 16, 128, 8, 8>();
-  // pass B candidates (N2)
-  reg_split<SPLIT_B_COLS, 15, 128, 128, 15>();
-  reg_split<SPLIT_B_COLS, 30, 64, 64, 30>();
-  reg_split<SPLIT_B_COLS, 16, 128, 128, 16>();
-  reg_split<SPLIT_B_ROWS, 128, 32, 256, 16, 8>();
-  reg_split<SPLIT_B_ROWS, 64, 32, 256, 8, 8>();
-  reg_split<SPLIT_B_ROWS, 256, 16, 256, 16, 16>();
+  static const bool done = [] {  // thread-safe one-time initialisation (see register_all, fast_registry.cu)
+    // pass A candidates (N1): <role, N, columns per tile, threads, super-stages...>
+    reg_split<SPLIT_A, 128, 16, 128, 16, 8>();
+    reg_split<SPLIT_A, 256, 16, 256, 16, 16>();
+    reg_split<SPLIT_A, 512, 16, 256, 32, 16>();
+    reg_split<SPLIT_A, 512, 16, 256, 8, 8, 8>();  // the reference's default bases for 7680 are [15, 8, 8, 8]
+    reg_split<SPLIT_A, 64, 16, 128, 8, 8>();
+    // pass B candidates (N2)
+    reg_split<SPLIT_B_COLS, 15, 128, 128, 15>();
+    reg_split<SPLIT_B_COLS, 30, 64, 64, 30>();
+    reg_split<SPLIT_B_COLS, 16, 128, 128, 16>();
+    reg_split<SPLIT_B_ROWS, 128, 32, 256, 16, 8>();
+    reg_split<SPLIT_B_ROWS, 64, 32, 256, 8, 8>();
+    reg_split<SPLIT_B_ROWS, 256, 16, 256, 16, 16>();
+    return true;
+  }();
+  (void)done;
 }
 
 struct SplitPass : Pass {
@@ -92,6 +93,11 @@ struct SplitPass : Pass {
 };
 
 }  // namespace
+
+size_t split_variant_count() {
+  register_split();
+  return split_registry().size();
+}
 
 std::unique_ptr<Pass> make_split_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src,
                                       bool scale_inverse, HalfMode half) {

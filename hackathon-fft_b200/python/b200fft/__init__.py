@@ -89,6 +89,7 @@ SYMBOLS = [
     ("b200fft_last_error", ctypes.c_char_p, []),
     ("b200fft_version", ctypes.c_int, []),
     ("b200fft_launch_count", ctypes.c_uint64, []),
+    ("b200fft_variant_count", ctypes.c_int, [ctypes.c_int]),
 ]
 
 

@@ -192,6 +192,10 @@ B200FFT_API const char* b200fft_last_error(void); /* thread-local detail of the 
 B200FFT_API int b200fft_version(void);
 /* total kernels launched by this library in this process (bench.py's gpu_launches) */
 B200FFT_API uint64_t b200fft_launch_count(void);
+/* number of compiled-in kernel variants: tier 0 = compile-time row / column variants, 1 = fused N-d kernels,
+ * 2 = two-pass split kernels; -1 for an unknown tier. Host-only (no CUDA call); safe to call from several threads at
+ * once, like plan creation: the variant tables are built exactly once. */
+B200FFT_API int b200fft_variant_count(int tier);
 
 #ifdef __cplusplus
 }

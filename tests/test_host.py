@@ -207,3 +207,34 @@ int main() {
                            str(src), "-o", str(exe), "-L", libdir, "-lb200fft", "-Wl,-rpath," + libdir])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
+
+def test_variant_tables_are_built_once_under_concurrent_first_use():
+    """include/b200fft.h promises that distinct plans may be created from distinct threads: the kernel-variant tables
+    behind plan creation must be built exactly once even when the FIRST calls race. A fresh process starts 16 threads
+    that all ask for the table sizes at the same moment (ctypes releases the GIL during the call)."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes, sys, threading
+L = ctypes.CDLL(sys.argv[1])
+L.b200fft_variant_count.restype = ctypes.c_int
+L.b200fft_variant_count.argtypes = [ctypes.c_int]
+start = threading.Barrier(16)
+seen = []
+def work():
+    start.wait()
+    seen.append(tuple(L.b200fft_variant_count(t) for t in (0, 1, 2)))
+ts = [threading.Thread(target=work) for _ in range(16)]
+[t.start() for t in ts]
+[t.join() for t in ts]
+assert len(set(seen)) == 1 and len(seen) == 16, seen
+print(*seen[0], L.b200fft_variant_count(7))
+'''
+    for _ in range(3):
+        r = subprocess.run([sys.executable, "-c", code, b200fft.lib_path()], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        fast, fused, split, unknown = (int(v) for v in r.stdout.split())
+        assert fast >= 40 and fused >= 10 and split >= 8 and unknown == -1, r.stdout
+    # and the in-process view agrees (tables are per process, sizes are a property of the build)
+    assert b200fft.lib().b200fft_variant_count(0) == fast
