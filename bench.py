@@ -213,34 +213,65 @@ def time_gpu(fn, warmup, steps, torch):
     return e0.elapsed_time(e1) / steps
 
 
-def cpu_reference_time(shape, real_in, workers, budget_s=12.0, repeats=2):
-    """Time the oracle (C++ port of the reference CPU path, workers=n) on a bounded sample
-    of the workload's batch; returns (ms for the FULL batch extrapolated linearly, sample batch, threads)."""
-    import oracle
-    threads = workers or oracle.hardware_threads()
-    per = int(np.prod(shape[1:]))
-    # size the sample from a quick probe
-    probe_b = max(1, min(shape[0], max(threads, 200000 // per)))
-    rng = np.random.default_rng(0)
-    comps = 1 if real_in else 2
-    x = rng.standard_normal((probe_b,) + tuple(shape[1:]) + (comps,)).astype(np.float32)
-    t0 = time.perf_counter()
-    oracle.ref_fft(x, workers=threads)
-    t_probe = time.perf_counter() - t0
-    sample_b = int(max(1, min(shape[0], probe_b * (budget_s / repeats) / max(t_probe, 1e-4))))
-    if sample_b != probe_b:
-        x = rng.standard_normal((sample_b,) + tuple(shape[1:]) + (comps,)).astype(np.float32)
+def _to_complex(x):
+    return x[..., 0] + 1j * x[..., 1] if x.shape[-1] == 2 else x[..., 0]
+
+
+def scipy_time(x, threads, repeats=2):
+    """Sanity CPU datapoint next to the port: scipy.fft.fftn (pocketfft, complex64) over all non-batch axes with
+    workers=n, the call benchmark-cpu-others/benchmark.py:35-49 times. Returns seconds per call (best of `repeats`)."""
+    import scipy.fft
+    xc = np.ascontiguousarray(_to_complex(x).astype(np.complex64))
+    axes = tuple(range(1, xc.ndim))
+    scipy.fft.fftn(xc, axes=axes, workers=threads)
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        oracle.ref_fft(x, workers=threads)
+        scipy.fft.fftn(xc, axes=axes, workers=threads)
         best = min(best, time.perf_counter() - t0)
-    return best * 1e3 * shape[0] / sample_b, sample_b, threads
+    return best
+
+
+def cpu_reference_time(shape, real_in, workers, budget_s=12.0, repeats=3):
+    """Time the oracle (C++ port of the reference CPU path, workers=n) on a bounded sample of the workload's batch.
+    Like the reference's own CPU bench (fft/bench.mojo:83-90) the plan — stage lists, twiddles, calc_buf — is built
+    OUTSIDE the timed region and only `fft(out, x, plan=plan)` into a preallocated output is timed.
+    Returns (ms for the FULL batch extrapolated linearly, sample batch, threads, scipy ms for the full batch)."""
+    import oracle
+    threads = workers or oracle.hardware_threads()
+    per = int(np.prod(shape[1:]))
+    comps = 1 if real_in else 2
+    rng = np.random.default_rng(0)
+
+    def timed(batch, reps):
+        x = rng.standard_normal((batch,) + tuple(shape[1:]) + (comps,)).astype(np.float32)
+        plan = oracle.RefPlan(x.shape, np.float32)
+        out = np.empty(plan.out_shape, np.float32)
+        plan.exec(out, x, workers=threads)  # warm-up: first touch of out / calc_buf, pool start
+        best = float("inf")
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            plan.exec(out, x, workers=threads)
+            best = min(best, time.perf_counter() - t0)
+        plan.destroy()
+        return best, x
+
+    probe_b = max(1, min(shape[0], max(threads * 8, 400000 // per)))
+    t_probe, x = timed(probe_b, 1)
+    sample_b = int(max(1, min(shape[0], probe_b * (budget_s / (repeats + 1)) / max(t_probe, 1e-5))))
+    best, x = timed(sample_b, repeats) if sample_b != probe_b else (t_probe, x)
+    sp_ms = None
+    try:
+        sp_ms = scipy_time(x, threads) * 1e3 * shape[0] / sample_b
+    except Exception:
+        pass
+    return best * 1e3 * shape[0] / sample_b, sample_b, threads, sp_ms
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port, all
-    host threads) on the same config / metric / unit. Rank 0 only under torchrun."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port, all host threads) on the same
+    config / metric / unit, timed the way the reference's bench_cpu_radix_n_rfft does (fft/bench.mojo:60-96): plan
+    built once outside the loop, each step = one fft(out, x, plan=plan) on a bounded sample. Rank 0 only under torchrun."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import oracle
@@ -248,11 +279,18 @@ def run_reference_arm(args):
     shape = PRIMARY["shape"]
     threads = oracle.hardware_threads()
     per = int(np.prod(shape[1:]))
-    # one step = a bounded sample of the workload: scale the batch so K+W steps end in minutes
     rng = np.random.default_rng(0)
-    probe = rng.standard_normal((max(threads, 64),) + tuple(shape[1:]) + (2,)).astype(np.float32)
+
+    def make(batch):
+        x = rng.standard_normal((batch,) + tuple(shape[1:]) + (2,)).astype(np.float32)
+        plan = oracle.RefPlan(x.shape, np.float32)
+        out = np.empty(plan.out_shape, np.float32)
+        plan.exec(out, x, workers=threads)
+        return x, out, plan
+
+    x, out, plan = make(max(threads * 8, 512))
     t0 = time.perf_counter()
-    oracle.ref_fft(probe, workers=threads)
+    plan.exec(out, x, workers=threads)
     t_probe = time.perf_counter() - t0
     total_steps = max(1, args.steps + args.warmup)
     # seconds of CPU work per step: bounded so the whole run ends within ~2 minutes (B200FFT_BENCH_REF_SECONDS
@@ -260,24 +298,34 @@ def run_reference_arm(args):
     target_s = min(20.0, 120.0 / total_steps)
     if os.environ.get("B200FFT_BENCH_REF_SECONDS"):
         target_s = float(os.environ["B200FFT_BENCH_REF_SECONDS"])
-    sample_b = int(max(1, min(shape[0], probe.shape[0] * target_s / max(t_probe, 1e-4))))
-    x = rng.standard_normal((sample_b,) + tuple(shape[1:]) + (2,)).astype(np.float32)
+    sample_b = int(max(1, min(shape[0], x.shape[0] * target_s / max(t_probe, 1e-5))))
+    if sample_b != x.shape[0]:
+        plan.destroy()
+        x, out, plan = make(sample_b)
     for _ in range(args.warmup):
-        oracle.ref_fft(x, workers=threads)
+        plan.exec(out, x, workers=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.ref_fft(x, workers=threads)
+        plan.exec(out, x, workers=threads)
     dt = (time.perf_counter() - t0) / args.steps
+    plan.destroy()
     gflops = flops_c2c((sample_b,) + tuple(shape[1:])) / dt / 1e9
     ms_full = dt * 1e3 * shape[0] / sample_b
+    scipy_gflops = None
+    try:
+        scipy_gflops = flops_c2c((sample_b,) + tuple(shape[1:])) / scipy_time(x, threads) / 1e9
+    except Exception:
+        pass
     line = {
         "impl": "reference", "metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": PRIMARY["name"], "note": "CPU reference path (workers=n): C++ port of the Mojo "
-                   "radix-n implementation (oracle/ref_fft.cpp); ms_per_step extrapolated to the full batch"},
+                   "radix-n implementation (oracle/ref_fft.cpp), plan built once outside the timed loop like "
+                   "fft/bench.mojo:83-90; ms_per_step extrapolated to the full batch"},
         "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": threads, "kind": "port",
-                         "sample": "%d of %d transforms of length %d per step" % (sample_b, shape[0], per)},
+                         "sample": "%d of %d transforms of length %d per step" % (sample_b, shape[0], per),
+                         "scipy_fft_workers_n_gflops": scipy_gflops},
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -510,11 +558,15 @@ def main():
     if not args.no_cpu:
         import oracle
         oracle.build()
-        cpu_ms, sample_b, threads = cpu_reference_time(shape, False, 0)
+        cpu_ms, sample_b, threads, sp_ms = cpu_reference_time(shape, False, 0)
         cpu = {"value": flops_c2c(shape) / cpu_ms / 1e6, "unit": "GFLOP/s", "cores": threads, "kind": "port",
                "ms_full_batch_extrapolated": cpu_ms,
-               "sample": "%d of %d transforms of length %d (oracle/ref_fft.cpp, workers=%d)" % (
-                   sample_b, shape[0], shape[1], threads)}
+               "sample": "%d of %d transforms of length %d (oracle/ref_fft.cpp, workers=%d; plan built outside the "
+                         "timed region, exec into a preallocated output, best of 3)" % (sample_b, shape[0], shape[1], threads),
+               "scipy_fft_workers_n": {"value": (flops_c2c(shape) / sp_ms / 1e6) if sp_ms else None, "unit": "GFLOP/s",
+                                       "ms_full_batch_extrapolated": sp_ms,
+                                       "note": "scipy.fft.fftn complex64 workers=n on the same sample (sanity datapoint, "
+                                               "benchmark-cpu-others/benchmark.py:35-49)"}}
 
     line = {
         "metric": METRIC, "value": gflops_total, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,

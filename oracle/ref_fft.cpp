@@ -24,12 +24,18 @@
 //                                            fft/fft/_fft.mojo:331-391 (unrolled form, N<=128)
 //   run_1d()                                 fft/fft/_ndim_fft_cpu.mojo:147-241
 //   transpose()                              fft/fft/_ndim_fft_cpu.mojo:63-93, _utils.mojo:400-419
-//   run_batch() / ref_exec()                 fft/fft/_ndim_fft_cpu.mojo:96-323
+//   Plan::exec() (run_batch)                 fft/fft/_ndim_fft_cpu.mojo:96-323
+//   Plan::init()                             fft/fft/_ndim_fft_cpu.mojo:28-60 (_CPUPlan), fft/fft/fft.mojo:122-157
+//   Pool / parallel_for                      std.algorithm.parallelize as used at _ndim_fft_cpu.mojo:306-308,323
+//   ref_plan_create / _exec / _destroy       the plan_fft(...) / fft(out, x, plan=plan) split timed by fft/bench.mojo:83-90
 #include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -309,11 +315,16 @@ inline bool run_stage_f32_avx2(const AxisPlan<float>& ax, size_t s, bool inverse
           acc = _mm256_fmadd_ps(wre, xv, t);
         }
         if (scale) acc = _mm256_mul_ps(acc, vinv1);
-        alignas(32) Cx<float> res[4];
-        _mm256_store_ps(reinterpret_cast<float*>(res), acc);
-        for (int l = 0; l < 4; ++l) {
-          const u64 mm = m + (u64)l;
-          out[(mm / P) * Q + k * P + mm % P] = res[l];
+        // out[(mm / P)*Q + k*P + mm % P] for mm = m..m+3, without a division per point
+        if (P == 1) {
+          alignas(32) Cx<float> res[4];
+          _mm256_store_ps(reinterpret_cast<float*>(res), acc);
+          Cx<float>* o = out + m * Q + k;
+          o[0] = res[0]; o[Q] = res[1]; o[2 * Q] = res[2]; o[3 * Q] = res[3];
+        } else {  // P == 2: two adjacent points per Q-block
+          float* o = reinterpret_cast<float*>(out + (m >> 1) * Q + k * 2);
+          _mm_storeu_ps(o, _mm256_castps256_ps128(acc));
+          _mm_storeu_ps(o + 2 * Q, _mm256_extractf128_ps(acc, 1));
         }
       }
     }
@@ -419,38 +430,127 @@ void transpose(Cx<T>* dst, const Cx<T>* src, u64 b, u64 M, u64 N) {
   }
 }
 
-// parallelize[func](n, workers) with a shared atomic counter
+// parallelize[func](n, workers): the reference hands its closures to the Mojo runtime's persistent worker pool
+// (std.algorithm.parallelize, used at _ndim_fft_cpu.mojo:306-308,323), so no thread is created per call. The same
+// here: one process-wide pool of sleeping workers; a job is a shared atomic index counter over [0, n).
+class Pool {
+ public:
+  static Pool& get() {
+    static Pool p;
+    return p;
+  }
+  template <class F>
+  void run(u64 n, u64 workers, F&& f) {
+    workers = std::max<u64>(1, std::min(workers, n));
+    if (workers == 1 || in_worker_) {  // nested parallelize from inside a job: run inline (see exec: the split makes
+      for (u64 i = 0; i < n; ++i) f(i);  // one of the two levels serial whenever the other has more than one worker)
+      return;
+    }
+    std::lock_guard<std::mutex> job_lock(job_mu_);  // one job at a time
+    grow(workers - 1);
+    std::atomic<u64> next(0);
+    const u64 grain = std::max<u64>(1, n / (workers * 8));
+    std::function<void()> body = [&]() {
+      for (;;) {
+        const u64 lo = next.fetch_add(grain);
+        if (lo >= n) break;
+        const u64 hi = std::min(n, lo + grain);
+        for (u64 i = lo; i < hi; ++i) f(i);
+      }
+    };
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      body_ = &body;
+      want_ = workers - 1;
+      started_ = 0;
+      done_ = 0;
+      ++gen_;
+    }
+    cv_.notify_all();
+    in_worker_ = true;  // the caller takes part in the job: a nested parallelize inside f runs inline
+    body();
+    in_worker_ = false;
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return done_ == want_; });
+    body_ = nullptr;
+  }
+
+ private:
+  Pool() {}
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void grow(u64 n) {
+    while (th_.size() < n) {
+      const u64 seen = gen_;
+      th_.emplace_back([this, seen] { loop(seen); });
+    }
+  }
+  void loop(u64 seen) {
+    in_worker_ = true;
+    for (;;) {
+      std::function<void()>* body = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        if (started_ >= want_) continue;  // this job needs fewer workers than the pool holds
+        ++started_;
+        body = body_;
+      }
+      (*body)();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        ++done_;
+      }
+      done_cv_.notify_one();
+    }
+  }
+  std::mutex job_mu_, mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> th_;
+  std::function<void()>* body_ = nullptr;
+  u64 gen_ = 0, want_ = 0, started_ = 0, done_ = 0;
+  bool stop_ = false;
+  static thread_local bool in_worker_;
+};
+thread_local bool Pool::in_worker_ = false;
+
 template <class F>
 void parallel_for(u64 n, u64 workers, F&& f) {
-  workers = std::max<u64>(1, std::min(workers, n));
-  if (workers == 1) {
-    for (u64 i = 0; i < n; ++i) f(i);
-    return;
-  }
-  std::atomic<u64> next(0);
-  const u64 grain = std::max<u64>(1, n / (workers * 8));
-  auto body = [&]() {
-    for (;;) {
-      u64 lo = next.fetch_add(grain);
-      if (lo >= n) break;
-      u64 hi = std::min(n, lo + grain);
-      for (u64 i = lo; i < hi; ++i) f(i);
-    }
-  };
-  std::vector<std::thread> th;
-  for (u64 w = 1; w < workers; ++w) th.emplace_back(body);
-  body();
-  for (auto& t : th) t.join();
+  Pool::get().run(n, workers, static_cast<F&&>(f));
 }
 
+// _CPUPlan (_ndim_fft_cpu.mojo:28-60) + the compile-time facts plan_fft fixes (fft.mojo:122-157): stage lists,
+// twiddle tables and the calc_buf scratch are built ONCE; exec() below is what the reference's bench times
+// (fft/bench.mojo:83-90: plan_fft outside, fft(out, x, plan=plan) inside the timed loop).
+struct PlanBase {
+  virtual ~PlanBase() {}
+  virtual int exec(const void* x, void* out, int workers) = 0;
+  bool f64 = false;
+};
+
 template <class T>
-int exec(const void* x, int in_dtype, int in_comps, T* out_raw, int64_t batches, int ndim,
-         const int64_t* dims, const uint32_t* bases_flat, const int32_t* bases_counts, int inverse,
-         int workers) {
-  if (ndim < 1 || batches < 1 || (in_comps != 1 && in_comps != 2)) return 1;
-  std::vector<AxisPlan<T>> axes(ndim);
+struct Plan : PlanBase {
+  std::vector<AxisPlan<T>> axes;
+  int in_dtype = IN_F32, in_comps = 2, ndim = 0, inverse = 0;
+  int64_t batches = 0;
   u64 prod = 1, total_stages = 0, max_batch_prod = 0;
-  {
+  std::vector<Cx<T>> calc;  // plan.calc_buf: one full copy of the output (_ndim_fft_cpu.mojo:44-45)
+
+  int init(int in_dtype_, int in_comps_, int64_t batches_, int ndim_, const int64_t* dims, const uint32_t* bases_flat,
+           const int32_t* bases_counts, int inverse_) {
+    if (ndim_ < 1 || batches_ < 1 || (in_comps_ != 1 && in_comps_ != 2)) return 1;
+    in_dtype = in_dtype_; in_comps = in_comps_; batches = batches_; ndim = ndim_; inverse = inverse_;
+    f64 = sizeof(T) == 8;
+    axes.resize(ndim);
     const uint32_t* bp = bases_flat;
     for (int a = 0; a < ndim; ++a) {
       AxisPlan<T>& ax = axes[a];
@@ -487,28 +587,20 @@ int exec(const void* x, int in_dtype, int in_comps, T* out_raw, int64_t batches,
       u64 mn = *std::min_element(user.begin(), user.end());
       max_batch_prod = std::max(max_batch_prod, ax.N / mn);
     }
+    total_stages += 2 * (u64)(ndim - 1);
+    calc.resize((size_t)batches * prod);
+    return 0;
   }
-  const int last_axis = ndim - 1;
-  total_stages += 2 * (u64)last_axis;
-
-  // worker split (_ndim_fft_cpu.mojo:125-140)
-  u64 threads = workers > 0 ? (u64)workers : std::max(1u, std::thread::hardware_concurrency());
-  u64 per_batch_workers = ndim > 1 ? std::min(threads, max_batch_prod) : 1;
-  u64 parallel_batches =
-      std::min<u64>(std::max<int64_t>((int64_t)threads - ((int64_t)per_batch_workers - 1), 1), (u64)batches);
-
-  std::vector<Cx<T>> calc((size_t)batches * prod);  // plan.calc_buf
-  Cx<T>* out_all = reinterpret_cast<Cx<T>*>(out_raw);
-  const size_t in_elem = (in_dtype == IN_U8 ? 1 : in_dtype == IN_F32 ? 4 : 8);
 
   // stages of axes to the right of `a` (_num_stages_end_of)
-  auto stages_from = [&](int a) {
+  u64 stages_from(int a) const {
     u64 s = 0;
     for (int k = a; k < ndim; ++k) s += axes[k].radix.size();
     return s;
-  };
+  }
 
-  auto run_1d = [&](int a, Cx<T>* lhs, Cx<T>* rhs, const void* xin) {
+  void run_1d(int a, Cx<T>* lhs, Cx<T>* rhs, const void* xin) const {
+    const int last_axis = ndim - 1;
     const AxisPlan<T>& ax = axes[a];
     const u64 prev = stages_from(a + 1) + (u64)(last_axis - a);
     for (size_t b = 0; b < ax.radix.size(); ++b) {
@@ -519,49 +611,68 @@ int exec(const void* x, int in_dtype, int in_comps, T* out_raw, int64_t batches,
       else src = {write_lhs ? rhs : lhs, nullptr, 0, 2};
       run_stage(ax, b, inverse != 0, src, write_lhs ? lhs : rhs);
     }
-  };
+  }
 
-  auto run_batch = [&](u64 bi) {
-    Cx<T>* base_out = out_all + bi * prod;
-    Cx<T>* base_calc = calc.data() + bi * prod;
-    const char* base_x = (const char*)x + (size_t)bi * prod * in_comps * in_elem;
-    if (ndim == 1) {
-      run_1d(0, base_out, base_calc, base_x);
-      return;
-    }
-    for (int a = last_axis; a >= 0; --a) {
-      const u64 dim = axes[a].N;
-      if (a != last_axis) {
-        // "into" transpose: [prod d<a][d_a][prod d>a] -> [prod d<a][prod d>a][d_a]
-        const u64 s = stages_from(a + 1) + (u64)(last_axis - (a + 1));
+  int exec(const void* x, void* out_raw, int workers) override {
+    const int last_axis = ndim - 1;
+    // worker split (_ndim_fft_cpu.mojo:125-140)
+    u64 threads = workers > 0 ? (u64)workers : std::max(1u, std::thread::hardware_concurrency());
+    u64 per_batch_workers = ndim > 1 ? std::min(threads, max_batch_prod) : 1;
+    u64 parallel_batches =
+        std::min<u64>(std::max<int64_t>((int64_t)threads - ((int64_t)per_batch_workers - 1), 1), (u64)batches);
+    Cx<T>* out_all = reinterpret_cast<Cx<T>*>(out_raw);
+    const size_t in_elem = (in_dtype == IN_U8 ? 1 : in_dtype == IN_F32 ? 4 : 8);
+
+    auto run_batch = [&](u64 bi) {
+      Cx<T>* base_out = out_all + bi * prod;
+      Cx<T>* base_calc = calc.data() + bi * prod;
+      const char* base_x = (const char*)x + (size_t)bi * prod * in_comps * in_elem;
+      if (ndim == 1) {
+        run_1d(0, base_out, base_calc, base_x);
+        return;
+      }
+      for (int a = last_axis; a >= 0; --a) {
+        const u64 dim = axes[a].N;
+        if (a != last_axis) {
+          // "into" transpose: [prod d<a][d_a][prod d>a] -> [prod d<a][prod d>a][d_a]
+          const u64 s = stages_from(a + 1) + (u64)(last_axis - (a + 1));
+          const bool write_lhs = (total_stages - (s + 1)) % 2 == 0;
+          u64 b = 1, n = 1;
+          for (int k = 0; k < a; ++k) b *= axes[k].N;
+          for (int k = a + 1; k < ndim; ++k) n *= axes[k].N;
+          if (write_lhs) transpose(base_out, base_calc, b, dim, n);
+          else transpose(base_calc, base_out, b, dim, n);
+        }
+        const u64 rows = prod / dim;
+        parallel_for(rows, per_batch_workers, [&](u64 r) {
+          run_1d(a, base_out + r * dim, base_calc + r * dim, base_x + (size_t)r * dim * in_comps * in_elem);
+        });
+      }
+      const u64 fft_stages = stages_from(0);
+      for (int a = 0; a < last_axis; ++a) {
+        // "restore" transpose: [prod d<a][prod d>a][d_a] -> [prod d<a][d_a][prod d>a]
+        const u64 s = fft_stages + (u64)last_axis + (u64)a;
         const bool write_lhs = (total_stages - (s + 1)) % 2 == 0;
         u64 b = 1, n = 1;
         for (int k = 0; k < a; ++k) b *= axes[k].N;
         for (int k = a + 1; k < ndim; ++k) n *= axes[k].N;
-        if (write_lhs) transpose(base_out, base_calc, b, dim, n);
-        else transpose(base_calc, base_out, b, dim, n);
+        if (write_lhs) transpose(base_out, base_calc, b, n, axes[a].N);
+        else transpose(base_calc, base_out, b, n, axes[a].N);
       }
-      const u64 rows = prod / dim;
-      parallel_for(rows, per_batch_workers, [&](u64 r) {
-        run_1d(a, base_out + r * dim, base_calc + r * dim,
-               base_x + (size_t)r * dim * in_comps * in_elem);
-      });
-    }
-    const u64 fft_stages = stages_from(0);
-    for (int a = 0; a < last_axis; ++a) {
-      // "restore" transpose: [prod d<a][prod d>a][d_a] -> [prod d<a][d_a][prod d>a]
-      const u64 s = fft_stages + (u64)last_axis + (u64)a;
-      const bool write_lhs = (total_stages - (s + 1)) % 2 == 0;
-      u64 b = 1, n = 1;
-      for (int k = 0; k < a; ++k) b *= axes[k].N;
-      for (int k = a + 1; k < ndim; ++k) n *= axes[k].N;
-      if (write_lhs) transpose(base_out, base_calc, b, n, axes[a].N);
-      else transpose(base_calc, base_out, b, n, axes[a].N);
-    }
-  };
+    };
+    parallel_for((u64)batches, parallel_batches, run_batch);
+    return 0;
+  }
+};
 
-  parallel_for((u64)batches, parallel_batches, run_batch);
-  return 0;
+template <class T>
+int exec(const void* x, int in_dtype, int in_comps, T* out_raw, int64_t batches, int ndim,
+         const int64_t* dims, const uint32_t* bases_flat, const int32_t* bases_counts, int inverse,
+         int workers) {
+  Plan<T> plan;
+  int rc = plan.init(in_dtype, in_comps, batches, ndim, dims, bases_flat, bases_counts, inverse);
+  if (rc) return rc;
+  return plan.exec(x, out_raw, workers);
 }
 
 int copy_bases(const std::vector<u64>& v, uint32_t* out, int cap) {
@@ -608,6 +719,30 @@ int ref_fft_exec_f64(const void* x, int in_dtype, int in_comps, double* out, int
   return exec<double>(x, in_dtype, in_comps, out, batches, ndim, dims, bases_flat, bases_counts,
                       inverse, workers);
 }
+
+// Plan handle: everything plan_fft builds once (stage lists, twiddles, calc_buf). out_f64 selects the working dtype.
+int ref_plan_create(void** plan, int out_f64, int in_dtype, int in_comps, int64_t batches, int ndim, const int64_t* dims,
+                    const uint32_t* bases_flat, const int32_t* bases_counts, int inverse) {
+  if (!plan) return 1;
+  *plan = nullptr;
+  int rc;
+  if (out_f64) {
+    auto* p = new Plan<double>();
+    rc = p->init(in_dtype, in_comps, batches, ndim, dims, bases_flat, bases_counts, inverse);
+    if (rc) delete p; else *plan = static_cast<PlanBase*>(p);
+  } else {
+    auto* p = new Plan<float>();
+    rc = p->init(in_dtype, in_comps, batches, ndim, dims, bases_flat, bases_counts, inverse);
+    if (rc) delete p; else *plan = static_cast<PlanBase*>(p);
+  }
+  return rc;
+}
+// fft(out, x, plan=plan, cpu_workers=workers): writes every element of the caller's `out`; nothing else is touched.
+int ref_plan_exec(void* plan, const void* x, void* out, int workers) {
+  if (!plan || !x || !out) return 1;
+  return static_cast<PlanBase*>(plan)->exec(x, out, workers);
+}
+void ref_plan_destroy(void* plan) { delete static_cast<PlanBase*>(plan); }
 
 int ref_hardware_threads(void) { return (int)std::max(1u, std::thread::hardware_concurrency()); }
 

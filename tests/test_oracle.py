@@ -120,6 +120,50 @@ def test_workers_do_not_change_result(oracle):
     assert np.array_equal(a, b)
 
 
+def test_plan_handle_is_reusable_and_writes_every_element(oracle):
+    """RefPlan = plan_fft once + fft(out, x, plan=plan) many times (what bench.py times): every call writes the whole
+    caller-provided output (pre-filled with NaN like tests.mojo:172-176) and gives the bits of the one-shot call,
+    for any worker count, also when calls with different inputs are interleaved on the same plan (calc_buf reuse)."""
+    rng = np.random.default_rng(21)
+    for shape, kw in [((37, 1024, 2), {}), ((5, 24, 20, 2), {}), ((3, 6, 4, 8, 1), {}), ((11, 93, 2), {"bases": [[31, 3]]}),
+                      ((4, 128, 2), {"inverse": True})]:
+        x1 = rng.standard_normal(shape).astype(np.float32)
+        x2 = rng.standard_normal(shape).astype(np.float32)
+        plan = oracle.RefPlan(shape, np.float32, **kw)
+        want1, want2 = oracle.ref_fft(x1, **kw), oracle.ref_fft(x2, **kw)
+        for workers in (1, 3, 8):
+            for x, want in ((x1, want1), (x2, want2), (x1, want1)):
+                out = np.full(plan.out_shape, np.nan, np.float32)
+                plan.exec(out, x, workers=workers)
+                assert np.array_equal(out, want), (shape, workers)
+        plan.destroy()
+    with pytest.raises(ValueError):
+        oracle.RefPlan((4, 100, 2), bases=[[7]])
+
+
+def test_plan_exec_from_many_threads(oracle):
+    """The worker pool is process-wide: concurrent execs of different plans serialise on it and stay correct."""
+    import threading
+    rng = np.random.default_rng(5)
+    xs = [rng.standard_normal((16, 256, 2)).astype(np.float32) for _ in range(4)]
+    wants = [oracle.ref_fft(x) for x in xs]
+    errs = []
+
+    def work(i):
+        plan = oracle.RefPlan(xs[i].shape)
+        out = np.empty(plan.out_shape, np.float32)
+        for _ in range(5):
+            plan.exec(out, xs[i], workers=4)
+            if not np.array_equal(out, wants[i]):
+                errs.append(i)
+        plan.destroy()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+
+
 def test_simd_path_is_bit_identical_to_the_scalar_restatement(oracle, tmp_path):
     """The oracle's AVX2 stage loops exist only to make the CPU baseline run at a realistic speed; they must give the
     same bits as the scalar restatement of the reference (same FMA sequence per output point). Build the file once

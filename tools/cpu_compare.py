@@ -86,7 +86,10 @@ def run_shape(shape, threads, budget_s, gpu):
     def oracle_first():
         o = oracle.ref_fft(x[:1])
         return o[0, ..., 0] + 1j * o[0, ..., 1]
-    leg("oracle_reference_cpu_path_all_threads", lambda: oracle.ref_fft(x, workers=threads), oracle_first)
+    rplan = oracle.RefPlan(x.shape, x.dtype)  # plan outside the timed calls, like fft/bench.mojo:83-90
+    rout = np.empty(rplan.out_shape, np.float32)
+    leg("oracle_reference_cpu_path_all_threads", lambda: rplan.exec(rout, x, workers=threads), oracle_first)
+    rplan.destroy()
 
     if gpu:
         import b200fft
