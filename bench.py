@@ -408,10 +408,24 @@ def bench_slab(n, world, rank, torch, dist, steps=10, warmup=3):
             t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-            # parity: energy (Parseval) of the distributed result against the input, reduced over ranks
+            # parity of the DISTRIBUTED result (b200fft.verify): (1) sampled bins — every rank's float64 share of the
+            # direct DFT sum, all-reduced, against the element the owning rank holds: sees accuracy and any systematic
+            # misplacement; (2) an impulse per source rank, exact spectrum compared at EVERY element of every slab: sees a
+            # single row in the wrong peer slot. Parseval (blind to permutations) is kept as a third figure.
+            from b200fft import verify
+            out = sl.forward(x).clone()
+            torch.cuda.synchronize()
+            bins_err = verify.sampled_bins_check(x, out, (n, n, n), rank, world)
+            dout = sl.forward(verify.delta_input((n, n, n), rank, world, x.device)).clone()
+            torch.cuda.synchronize()
+            delta_err = verify.delta_volume_check(dout, (n, n, n), rank, world)
+            del dout
             e = torch.stack([out.double().pow(2).sum(), x.double().pow(2).sum()])
             dist.all_reduce(e)
             res[mode] = {"ms": ms, "gflops": 5.0 * n ** 3 * math.log2(n ** 3) / ms / 1e6,
+                         "sampled_bins_max_rel_err": bins_err, "sampled_bins": 32,
+                         "delta_volume_max_rel_err": delta_err,
+                         "parity_ok": bool(bins_err < 2e-6 and delta_err < 2e-6),
                          "parseval_rel_err": abs(float(e[0] / (e[1] * n ** 3)) - 1.0)}
             if mode == "fused":
                 res[mode]["peer_wait_timeouts"] = sl.timeouts()

@@ -85,6 +85,62 @@ def test_slab_decomposition_world2_gloo(tmp_path, dims):
         assert np.linalg.norm(got - ref) <= 2e-6 * np.linalg.norm(ref)
 
 
+def _verify_worker(rank, world, port, dims, out_dir):
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "hackathon-fft_b200", "python")]
+    from b200fft.slab import SlabFFT3D
+    from b200fft import verify
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Z, Y, X = dims
+    zl, yl = Z // world, Y // world
+    x = torch.from_numpy(np.random.default_rng(7 + rank).standard_normal((zl, Y, X, 2)).astype(np.float32))
+    slab = SlabFFT3D(dims, exchange="nccl", engine=NumpyEngine(dims, world))
+    out = slab.forward(x).clone()
+    res = {"good": verify.sampled_bins_check(x, out, dims, rank, world)}
+    d = verify.delta_input(dims, rank, world, "cpu")
+    dout = slab.forward(d).clone()
+    res["good_delta"] = verify.delta_volume_check(dout, dims, rank, world)
+
+    def energy(t):
+        e = t.double().pow(2).sum().reshape(1)
+        dist.all_reduce(e)
+        return float(e)
+
+    # (a) rank 0's block of z planes and rank 1's land in each other's slot of the receive slab (a wrong zbase)
+    bad = torch.cat([out[zl:2 * zl], out[:zl], out[2 * zl:]], 0)
+    dbad = torch.cat([dout[zl:2 * zl], dout[:zl], dout[2 * zl:]], 0)
+    res["swapped_z_blocks"] = verify.sampled_bins_check(x, bad, dims, rank, world)
+    res["swapped_z_blocks_delta"] = verify.delta_volume_check(dbad, dims, rank, world)
+    res["swapped_parseval_ratio"] = energy(bad) / energy(out)
+    # (b) ONE y row of ONE rank lands in the neighbouring row's place: only the full-coverage check must see it
+    one = dout.clone()
+    if rank == world - 1:
+        one[:, [0, 1]] = one[:, [1, 0]]
+    res["one_row_delta"] = verify.delta_volume_check(one, dims, rank, world)
+    if rank == 0:
+        with open(os.path.join(out_dir, "verify.json"), "w") as f:
+            json.dump(res, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dims", [(2, (8, 12, 6)), (4, (16, 8, 10))])
+def test_distributed_checks_see_misplaced_blocks_that_parseval_cannot(tmp_path, world, dims):
+    """b200fft.verify (what bench.py's slab leg and the multi-GPU test report): ~1e-7 on a correct result, O(1) when
+    blocks are permuted although the energy is unchanged."""
+    import json
+    mp.spawn(_verify_worker, args=(world, _free_port(), dims, str(tmp_path)), nprocs=world, join=True)
+    res = json.load(open(os.path.join(str(tmp_path), "verify.json")))
+    assert res["good"] < 2e-6 and res["good_delta"] < 2e-6, res
+    assert abs(res["swapped_parseval_ratio"] - 1.0) < 1e-12          # Parseval is blind to it
+    assert res["swapped_z_blocks"] > 0.1 and res["swapped_z_blocks_delta"] > 0.1, res
+    assert res["one_row_delta"] > 0.1, res
+
+
 def test_slab_rejects_indivisible_dims_and_cpu_product_path():
     import b200fft
     from b200fft.slab import SlabFFT3D
