@@ -69,8 +69,10 @@ std::unique_ptr<Pass> make_pass(b200fft_plan* plan, int axis, const AxisView& vi
   const Problem& p = plan->prob;
   std::unique_ptr<Pass> pass;
   if (!(p.desc.flags & B200FFT_FLAG_FORCE_GENERIC)) {
-    pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
-    if (!pass) pass = make_split_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+    if (!(p.desc.flags & B200FFT_FLAG_FORCE_RT)) {
+      pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+      if (!pass) pass = make_split_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+    }
     if (!pass) pass = make_rt_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
   }
   if (!pass) pass = make_generic_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
@@ -321,21 +323,12 @@ int b200fft_plan_destroy(b200fft_plan* plan) {
 // work_batch0: first batch item of this call inside the plan-wide workspace (exec_host chunks)
 static int run_passes(b200fft_plan* plan, void* d_out, const void* d_in, int64_t nbatch, cudaStream_t st,
                       int64_t work_batch0 = 0) {
-  const Problem& p = plan->prob;
-  const size_t in_stride = (size_t)p.in_scalars_per_batch * p.in_elem;
-  const size_t out_stride = (size_t)p.out_scalars_per_batch * p.out_elem;
-  const int64_t chunk = plan->chunk_batches > 0 ? plan->chunk_batches : nbatch;
-  for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
-    const int64_t nb = std::min<int64_t>(chunk, nbatch - b0);
-    char* out_b = (char*)d_out + (size_t)b0 * out_stride;
-    const char* in_b = (const char*)d_in + (size_t)b0 * in_stride;
-    char* work_b = (char*)plan->workspace + (size_t)(b0 + work_batch0) * plan->work_stride;
-    for (auto& pass : plan->passes) {
-      const void* src = pass->src_sel == BUF_INPUT ? (const void*)in_b : pass->src_sel == BUF_WORK ? (const void*)work_b : (const void*)out_b;
-      void* dst = pass->dst_sel == BUF_WORK ? (void*)work_b : (void*)out_b;
-      int rc = pass->launch(src, dst, nb, st);
-      if (rc != B200FFT_OK) return rc;
-    }
+  char* work = (char*)plan->workspace + (size_t)work_batch0 * plan->work_stride;
+  for (auto& pass : plan->passes) {
+    const void* src = pass->src_sel == BUF_INPUT ? d_in : pass->src_sel == BUF_WORK ? (const void*)work : (const void*)d_out;
+    void* dst = pass->dst_sel == BUF_WORK ? (void*)work : d_out;
+    int rc = pass->launch(src, dst, nbatch, st);
+    if (rc != B200FFT_OK) return rc;
   }
   return B200FFT_OK;
 }
@@ -368,6 +361,21 @@ int b200fft_exec_scatter(b200fft_plan* plan, void* const* peer_out, int npeers, 
   sc.npeers = npeers;
   sc.my_rank = my_rank;
   return last.launch_scatter(last.src_sel == BUF_INPUT ? d_in : (const void*)d_work, sc, plan->prob.batch, st);
+}
+
+int b200fft_stream_synchronize(void* cu_stream) {
+  B200_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)cu_stream));
+  return B200FFT_OK;
+}
+
+int b200fft_host_register(void* h_ptr, size_t bytes) {
+  if (!h_ptr || !bytes) return fail(B200FFT_ERR_INVALID_ARG, "null host range");
+  B200_CUDA_CHECK(cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable));
+  return B200FFT_OK;
+}
+int b200fft_host_unregister(void* h_ptr) {
+  B200_CUDA_CHECK(cudaHostUnregister(h_ptr));
+  return B200FFT_OK;
 }
 
 int b200fft_malloc(void** d_ptr, size_t bytes) {
@@ -415,7 +423,6 @@ int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in) {
     int64_t nchunks = (int64_t)(((size_t)p.batch * per + (chunk_mb << 20) - 1) / (chunk_mb << 20));
     nchunks = std::min<int64_t>(64, std::max<int64_t>(4, nchunks));
     int64_t chunk = std::max<int64_t>(1, (p.batch + nchunks - 1) / nchunks);
-    if (plan->chunk_batches > 0) chunk = ((chunk + plan->chunk_batches - 1) / plan->chunk_batches) * plan->chunk_batches;
     plan->host_chunk = chunk;
     // each resource is created only while still null, so a call that failed half way through can be retried
     // without leaking what it had already made (b200fft_plan_destroy frees whatever exists)
@@ -472,7 +479,6 @@ size_t b200fft_plan_describe(const b200fft_plan* plan, char* buf, size_t cap) {
   if (!plan) return 0;
   std::string text;
   for (auto& pass : plan->passes) text += pass->describe() + "\n";
-  if (plan->chunk_batches > 0) text += "chunk_batches=" + std::to_string(plan->chunk_batches) + "\n";
   if (buf && cap) {
     strncpy(buf, text.c_str(), cap - 1);
     buf[cap - 1] = 0;
@@ -482,10 +488,9 @@ size_t b200fft_plan_describe(const b200fft_plan* plan, char* buf, size_t cap) {
 
 int b200fft_plan_launches(const b200fft_plan* plan) {
   if (!plan) return 0;
-  int per_chunk = 0;
-  for (auto& pass : plan->passes) per_chunk += pass->launches();
-  const int64_t chunk = plan->chunk_batches > 0 ? plan->chunk_batches : plan->prob.batch;
-  return per_chunk * (int)((plan->prob.batch + chunk - 1) / chunk);
+  int n = 0;
+  for (auto& pass : plan->passes) n += pass->launches();
+  return n;
 }
 
 size_t b200fft_plan_in_bytes(const b200fft_plan* plan) {

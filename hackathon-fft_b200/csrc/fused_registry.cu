@@ -182,8 +182,9 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
   // per-axis kernels (default_min_batch > 0: 64^3 at every batch, 128^3 from batch 4; profiles/r1_fused_v1.md)
   int mode_env = -1;
   if (const char* e = getenv("B200FFT_FUSED")) mode_env = atoi(e) != 0;
+  if (p.desc.flags & (B200FFT_FLAG_FORCE_GENERIC | B200FFT_FLAG_NO_FUSED | B200FFT_FLAG_FORCE_RT)) return nullptr;
+  if (p.desc.flags & B200FFT_FLAG_PREFER_FUSED) mode_env = 1;
   if (mode_env == 0) return nullptr;
-  if (p.desc.flags & (B200FFT_FLAG_FORCE_GENERIC | B200FFT_FLAG_NO_FUSED)) return nullptr;
   if (p.desc.out_dtype != B200FFT_F32 || p.desc.in_dtype != B200FFT_F32) return nullptr;
   if (p.rank < 2 || p.rank > 3) return nullptr;
   for (auto& ax : p.axes)

@@ -28,7 +28,7 @@ struct IoSpec {
 
 // Peer scatter for the slab exchange fused into the last pass's store.
 struct Scatter {
-  void* const* peer_out = nullptr;  // device-visible array of npeers base pointers (device memory)
+  void* const* peer_out = nullptr;  // HOST array of npeers device pointers (copied into the kernel's arguments)
   int npeers = 0;
   int my_rank = 0;
 };
@@ -71,7 +71,6 @@ struct b200fft_plan {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   size_t work_stride = 0;     // workspace bytes per batch item
-  int64_t chunk_batches = 0;  // >0: run all passes per chunk of this many batch items (L2 residency)
   // exec_host resources (lazily created)
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   void* h_dev_in[2] = {nullptr, nullptr};

@@ -17,12 +17,24 @@ import ctypes
 import os
 
 __all__ = ["plan_fft", "fft", "Plan", "SlabPlan", "B200FFTError", "ordered_bases", "default_bases", "dry_run",
-           "launch_count", "lib_path", "REAL_FULL", "REAL_HALF", "FLAG_FORCE_GENERIC", "FLAG_NO_CHUNKING", "FLAG_NO_FUSED"]
+           "launch_count", "lib_path", "REAL_FULL", "REAL_HALF", "FLAG_FORCE_GENERIC", "FLAG_NO_FUSED", "FLAG_PREFER_FUSED",
+           "FLAG_FORCE_RT", "GPUTest", "stream_synchronize", "host_register", "host_unregister"]
 
 MAX_RANK = 8
 U8, F32, F64 = 0, 1, 2
 REAL_FULL, REAL_HALF = 0, 1
-FLAG_FORCE_GENERIC, FLAG_NO_CHUNKING, FLAG_NO_FUSED = 1, 2, 4
+FLAG_FORCE_GENERIC, FLAG_NO_FUSED, FLAG_PREFER_FUSED, FLAG_FORCE_RT = 1, 4, 8, 16
+
+
+class GPUTest:
+    """The reference's `_GPUTest` path forcer (_ndim_fft_gpu.mojo:453-459) mapped onto this library's kernel tiers,
+    so the same small vectors exercise each of them (fft/tests.mojo:398-417):
+        BLOCK       -> one compile-time tile kernel per axis (no fused N-d kernel)
+        WARP        -> the runtime-length tier (rt.cu)
+        DEVICE_WIDE -> the fused N-d persistent kernel wherever a variant matches (device-wide dependency counters)
+        CLUSTER     -> the generic per-output-point kernel (the reference's own formulation)"""
+    BLOCK, WARP, DEVICE_WIDE, CLUSTER = 0, 1, 2, 3
+    FLAGS = {0: FLAG_NO_FUSED, 1: FLAG_FORCE_RT, 2: FLAG_PREFER_FUSED, 3: FLAG_FORCE_GENERIC}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libb200fft.so"))
@@ -60,6 +72,9 @@ SYMBOLS = [
     ("b200fft_plan_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_Desc)]),
     ("b200fft_exec", ctypes.c_int, [_vp, _vp, _vp, _vp]),
     ("b200fft_exec_host", ctypes.c_int, [_vp, _vp, _vp]),
+    ("b200fft_stream_synchronize", ctypes.c_int, [_vp]),
+    ("b200fft_host_register", ctypes.c_int, [_vp, ctypes.c_size_t]),
+    ("b200fft_host_unregister", ctypes.c_int, [_vp]),
     ("b200fft_exec_scatter", ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     ("b200fft_malloc", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_size_t]),
     ("b200fft_free", ctypes.c_int, [_vp]),
@@ -153,6 +168,20 @@ def ipc_open(handle):
 
 def ipc_close(ptr):
     _check(lib().b200fft_ipc_close(ptr))
+
+
+def stream_synchronize(stream=None):
+    """Block until `stream` (None = the legacy default stream) is idle: b200fft_stream_synchronize."""
+    _check(lib().b200fft_stream_synchronize(_ptr(stream)))
+
+
+def host_register(arr):
+    """Page-lock a caller-owned host array so exec_host's copies overlap the kernels (cudaHostRegister)."""
+    _check(lib().b200fft_host_register(_ptr(arr), arr.nbytes))
+
+
+def host_unregister(arr):
+    _check(lib().b200fft_host_unregister(_ptr(arr)))
 
 
 def ordered_bases(length, bases):
@@ -369,11 +398,11 @@ def plan_fft(in_dtype, out_dtype, in_layout, out_layout, *, bases=None, inverse=
     `bases`: one list of radix bases per axis (any primes / composites whose powers multiply
     to the axis length); None = the reference's default rule. `runtime_twfs` and
     `max_cluster_size` are accepted for signature compatibility and ignored (twiddles always
-    come from device tables here). `_test="generic"` forces the generic kernel, the analogue
-    of the reference's `_GPUTest` path forcer.
+    come from device tables here). `_test`: a GPUTest value forces a kernel tier (the role of the
+    reference's `Optional[_GPUTest]`); any other non-None value forces the generic kernel.
     """
     if _test is not None:
-        flags |= FLAG_FORCE_GENERIC
+        flags |= GPUTest.FLAGS.get(_test, FLAG_FORCE_GENERIC) if isinstance(_test, int) else FLAG_FORCE_GENERIC
     d, keep = _make_desc(in_dtype, out_dtype, in_layout, out_layout, bases, inverse, real_mode, axis_mask, device, flags)
     h = ctypes.c_void_p()
     _check(lib().b200fft_plan_create(ctypes.byref(h), ctypes.byref(d)))

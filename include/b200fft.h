@@ -68,11 +68,18 @@ enum {
   /* Force the generic runtime-radix kernel for every axis (debug knob; plays the
      role of the reference's `_test: _GPUTest` path forcer, _ndim_fft_gpu.mojo:453-459). */
   B200FFT_FLAG_FORCE_GENERIC = 1u << 0,
-  /* Disable L2-resident chunking of multi-pass N-d transforms. */
-  B200FFT_FLAG_NO_CHUNKING = 1u << 1,
+  /* (bit 1 reserved: it named a chunking switch that round 1 never implemented) */
   /* Never use the fused N-d kernel (one persistent kernel for all axes, intermediate kept in L2):
      run one kernel per axis instead. b200fft_exec_scatter needs per-axis passes. */
-  B200FFT_FLAG_NO_FUSED = 1u << 2
+  B200FFT_FLAG_NO_FUSED = 1u << 2,
+  /* Use the fused N-d kernel whenever a variant matches the problem, not only where it was measured to win
+     (what the environment variable B200FFT_FUSED=1 does process-wide). */
+  B200FFT_FLAG_PREFER_FUSED = 1u << 3,
+  /* Skip the compile-time kernels: run every axis on the runtime-length tier (rt.cu), falling back to the generic
+     kernel where that tier does not apply. With FORCE_GENERIC / NO_FUSED / PREFER_FUSED this lets one small
+     problem exercise every kernel tier, the job `_GPUTest.{BLOCK,WARP,DEVICE_WIDE,CLUSTER}` does in the
+     reference (_ndim_fft_gpu.mojo:453-459, fft/tests.mojo:398-417). */
+  B200FFT_FLAG_FORCE_RT = 1u << 4
 };
 
 /*
@@ -111,10 +118,22 @@ B200FFT_API int b200fft_plan_create(b200fft_plan** plan, const b200fft_desc* des
  * same element type and component count. */
 B200FFT_API int b200fft_exec(b200fft_plan* plan, void* d_out, const void* d_in, void* cu_stream);
 
-/* Same transform with HOST buffers: pinned staging, chunked H2D -> kernels -> D2H
- * overlapped on internal streams; returns after the result is in h_out. This is the
- * end-to-end call bench.py times as `e2e`. */
+/* Blocks until everything enqueued on `cu_stream` has finished (NULL = the legacy default stream, which is
+ * where b200fft_exec launches when it is given NULL). A host language whose device context does not expose its
+ * CUstream calls exec with NULL and then this, so that correctness never depends on whether the context's own
+ * stream is a blocking one (the Mojo wrapper does: hackathon-fft_b200/mojo/fft/fft/_ndim_fft_gpu.mojo). */
+B200FFT_API int b200fft_stream_synchronize(void* cu_stream);
+
+/* Same transform with HOST buffers, cut into chunks that flow H2D -> kernels -> D2H on three internal streams
+ * with two device buffers per direction; returns after the result is in h_out. The copies are issued straight
+ * from / into the caller's memory: pass page-locked buffers (b200fft_host_register, cudaHostAlloc, torch
+ * pin_memory) for the copies to run asynchronously and overlap the kernels — with pageable memory the call is
+ * still correct but each copy is staged by the driver and serialises. This is the end-to-end call bench.py
+ * times as `e2e`, and what the Mojo package's host-tensor overloads of `fft` call. */
 B200FFT_API int b200fft_exec_host(b200fft_plan* plan, void* h_out, const void* h_in);
+/* Page-lock / unlock a caller-owned host range (cudaHostRegister) so exec_host's copies overlap. */
+B200FFT_API int b200fft_host_register(void* h_ptr, size_t bytes);
+B200FFT_API int b200fft_host_unregister(void* h_ptr);
 
 /* Slab-decomposition step 1 with the exchange fused into the last pass (multi-GPU, one process
  * per GPU). The plan is the LOCAL transform of this rank's slab, e.g. batch = local z planes,
