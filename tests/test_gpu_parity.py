@@ -33,7 +33,7 @@ def c2(a):
     return a[..., 0] + 1j * a[..., 1]
 
 
-def run_gpu(x, *, bases=None, inverse=False, out_dtype=np.float32, generic=False, nan_fill=True):
+def run_gpu(x, *, bases=None, inverse=False, out_dtype=np.float32, generic=False, nan_fill=True, tier=None, describe=None):
     """plan_fft + fft on device buffers; output prefilled with NaN like the reference's
     tests (tests.mojo:219-222) to catch unwritten elements."""
     import torch
@@ -42,7 +42,9 @@ def run_gpu(x, *, bases=None, inverse=False, out_dtype=np.float32, generic=False
     tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64
     out = torch.full(out_layout, float("nan"), dtype=tdt, device="cuda")
     plan = b200fft.plan_fft(str(x.dtype), np.dtype(out_dtype).name, x.shape, out_layout, bases=bases,
-                            inverse=inverse, _test=("generic" if generic else None))
+                            inverse=inverse, _test=(tier if tier is not None else "generic" if generic else None))
+    if describe is not None:
+        describe.append(plan.describe())
     b200fft.fft(out, xt, plan=plan)
     torch.cuda.synchronize()
     res = out.cpu().numpy()
@@ -82,6 +84,32 @@ def test_nd_golden_uint8(golden, key, dtype, generic):
     want = np.array(d["X"], dtype=np.float64).reshape([1] + d["dims"] + [2])
     got = run_gpu(x, out_dtype=dtype, generic=generic)
     np.testing.assert_allclose(got, want, atol=golden["atol"], rtol=golden["rtol"])
+
+
+@pytest.mark.parametrize("tier", [b200fft.GPUTest.BLOCK, b200fft.GPUTest.WARP, b200fft.GPUTest.DEVICE_WIDE,
+                                  b200fft.GPUTest.CLUSTER])
+def test_gpu_test_tiers_on_the_golden_vectors(golden, tier):
+    """fft/tests.mojo:398-417 runs its vectors once per `_GPUTest` value; here each value forces one kernel tier of
+    this library (b200fft.GPUTest) and the plan's description shows the tier really ran."""
+    names = {b200fft.GPUTest.BLOCK: ("rows", "cols"), b200fft.GPUTest.WARP: ("rt_", "generic"),
+             b200fft.GPUTest.DEVICE_WIDE: ("fused", "rows", "cols"), b200fft.GPUTest.CLUSTER: ("generic",)}[tier]
+    for length, bases in CASES[::3]:
+        vs = golden["vectors_1d"][str(length)]
+        x = np.array([v["x"] for v in vs], dtype=np.float32)[:, :, None]
+        spec = np.array([v["X"] for v in vs], dtype=np.float64)
+        text = []
+        got = run_gpu(x, bases=[list(bases)], tier=tier, describe=text)
+        np.testing.assert_allclose(got, spec, atol=golden["atol"], rtol=golden["rtol"], err_msg=str((length, bases)))
+        if tier in (b200fft.GPUTest.WARP, b200fft.GPUTest.CLUSTER):
+            assert any(n in text[0] for n in names), text[0]
+    # a shape every tier covers, N-d: the fused kernel really is picked by DEVICE_WIDE and never by BLOCK
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 64, 64, 64, 2)).astype(np.float32)
+    text = []
+    got = run_gpu(x, tier=tier, describe=text)
+    check_vs(got, np.fft.fftn(c2(x), axes=(1, 2, 3)), RTOL_L2_NP, RTOL_MAX_NP)
+    assert ("fused" in text[0]) == (tier == b200fft.GPUTest.DEVICE_WIDE), text[0]
+    assert any(n in text[0] for n in names), text[0]
 
 
 RANDOM_SHAPES = [
