@@ -117,10 +117,16 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
     return B200FFT_OK;
   };
 
-  // one persistent kernel for all axes when a fused variant covers the problem (fused_registry.cu)
-  if (!dry) {
+  // one persistent kernel for all axes when a fused variant covers the problem (fused_registry.cu); the per-axis
+  // passes are still built and kept behind it as its fallback (a refused cooperative launch)
+  if (!dry && !plan->building_fallback) {
     std::unique_ptr<Pass> fused = make_fused_pass(*plan);
     if (fused) {
+      plan->building_fallback = true;
+      const int rc = build_passes(plan, false, nullptr);
+      plan->building_fallback = false;
+      if (rc == B200FFT_OK) fused->fallback = std::move(plan->passes);
+      plan->passes.clear();
       plan->passes.push_back(std::move(fused));
       return B200FFT_OK;
     }

@@ -354,8 +354,8 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   }
   std::vector<float2> tw = build_twiddles(v->radices, half == HALF_NONE ? pass->inverse : half == HALF_C2R);
   if (cudaMalloc(&pass->d_tw, tw.size() * sizeof(float2)) != cudaSuccess) return nullptr;
+  plan.owned_device.push_back(pass->d_tw);  // owned by the plan BEFORE the copy: a failed copy must not leak it
   if (cudaMemcpy(pass->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
-  plan.owned_device.push_back(pass->d_tw);
   std::string stages;
   for (uint32_t r : ax.ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
   char buf[320];

@@ -53,6 +53,7 @@ struct NdArgs {
   const NdSegment* segs;
   unsigned total_items;
   unsigned* ctrl;                 // [0] next item, [1] CTAs finished, then the group counters
+  unsigned* err;                  // mapped HOST word: set to 1 when a dependency wait gave up (checked by the next exec)
   int cnt_off[ND_MAX_PHASES];     // offset of each phase's counters inside ctrl
   int nwords;                     // words to clear at the end (header + counters)
 };
@@ -62,13 +63,19 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Spin until *cnt >= want. Every tile only waits for tiles that were handed out earlier, so the wait always ends;
-// should a bug ever break that, the kernel traps after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void wait_counter_gpu(const unsigned* cnt, unsigned want, unsigned sleep_ns) {
+// Spin until *cnt >= want. Every tile only waits for tiles that were handed out earlier (v1: in-order atomic fetch;
+// v2: static assignment with the whole grid co-resident, guaranteed by the cooperative launch), so the wait always
+// ends. Should that ever be violated, the wait gives up after ~2 s, raises the plan's sticky error word (a mapped
+// host word the next b200fft_exec reads and reports) and the kernel runs to its end with invalid results: no trap,
+// so the CUDA context survives.
+__device__ __forceinline__ void wait_counter_gpu(const unsigned* cnt, unsigned want, unsigned sleep_ns, unsigned* err) {
   unsigned spins = 0;
   while (ld_acquire_gpu(cnt) < want) {
     __nanosleep(sleep_ns);
-    if (++spins > 30000000u) __trap();
+    if (++spins > 30000000u) {
+      if (err) atomicExch_system(err, 1u);
+      return;
+    }
   }
 }
 
@@ -201,7 +208,7 @@ __device__ __forceinline__ void nd_do_phase(const NdArgs& a, long long gtile, fl
       const NdPhase& Q = a.ph[PH - 1];
       const unsigned* cnt = a.ctrl + a.cnt_off[PH - 1] + t * Q.groups_per_transform + tile / P.dep_div;
       const unsigned want = (unsigned)Q.tiles_per_group;
-      wait_counter_gpu(cnt, want, 64);
+      wait_counter_gpu(cnt, want, 64, a.err);
     }
     __syncthreads();
   }

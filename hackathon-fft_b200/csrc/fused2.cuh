@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(NT + 32, MINB)
 
   if (threadIdx.x >= NT) {
     // ---------------- producer warp (lane 0). Work is assigned statically, CTA c takes items c, c + G, c + 2G, ...
-    // of the global order (the grid is sized to be fully resident, so every item's producers are running or done):
+    // of the global order (the launch is COOPERATIVE, so the whole grid is co-resident and every item's producers are
+    // running or done; fused_registry.cu falls back to the per-axis kernels when such a launch is refused):
     // no atomic work fetch, and item k+1 is resolved — segment lookup, dependency counter read with ld.acquire —
     // while the consumers still work on item k, so neither global round trip sits between two copies. Claiming
     // several items per atomic instead was measured slower: it reserves work far ahead of execution and breaks
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(NT + 32, MINB)
           tma::mbar_arrive(&full[slot]);
           break;
         }
-        if (!r.ready) wait_counter_gpu(r.cnt, r.want, 32);
+        if (!r.ready) wait_counter_gpu(r.cnt, r.want, 32, a.err);
         if (r.phase > 0) tma::fence_proxy_async_all();
         void* in_buf = base + slot * IN;
         if (r.phase == 0) nd_issue<0, P0>(a, nullptr, r, in_buf, &full[slot], &ring[slot]);

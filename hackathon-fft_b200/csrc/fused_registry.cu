@@ -9,6 +9,8 @@
 //   B200FFT_CHUNK_MB=<n>   pipeline chunk size (default 8): how much phase-0 output is produced per
 //                          round; ~2-3 chunks are live in L2 at any time
 //   B200FFT_FUSED_PREFER=substr   prefer variants whose name contains substr (tuning aid)
+// The v2 kernels (static work assignment) are launched COOPERATIVELY: the driver guarantees the whole grid is
+// co-resident or refuses the launch, in which case the pass runs the plan's per-axis kernels instead (Pass::fallback).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -46,27 +48,6 @@ void register_all_fused() {
     return true;
   }();
   (void)done;
-}
-
-// Two persistent kernels with STATIC work assignment (fused2.cuh) must not share the SMs: each sizes its grid
-// to the whole device, and with both only partly resident the resident CTAs of each could spin on tiles owned by
-// CTAs that cannot be scheduled. Launches of such kernels are therefore chained device-wide (all streams of this
-// process) through one event per device; kernels with dynamic in-order work fetch (fused.cuh, slab.cuh) do not
-// need it. B200FFT_FUSED_SERIALIZE=0 disables the chaining (e.g. for CUDA-graph capture of a single stream).
-struct FusedChain {
-  std::mutex mu;
-  cudaEvent_t ev[64] = {};
-};
-FusedChain& fused_chain() {
-  static FusedChain c;
-  return c;
-}
-bool fused_serialize() {
-  static const bool on = [] {
-    const char* e = getenv("B200FFT_FUSED_SERIALIZE");
-    return !e || atoi(e) != 0;
-  }();
-  return on;
 }
 
 long long prod(const std::vector<long long>& v, size_t a, size_t b) {
@@ -124,8 +105,30 @@ struct FusedPass : Pass {
     return B200FFT_OK;
   }
 
+  unsigned* h_err = nullptr;  // mapped host word the kernels raise when a dependency wait gives up
+  unsigned* d_err = nullptr;
+  bool use_fallback = false;  // a cooperative launch was refused once: stay on the per-axis kernels
+
+  int run_fallback(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) {
+    if (fallback.empty()) return fail(B200FFT_ERR_CUDA, "%s cannot be launched and the plan has no per-axis passes", v->name.c_str());
+    for (auto& p : fallback) {
+      int rc = p->launch(p->src_sel == BUF_INPUT ? src : (const void*)dst, dst, nbatch, stream);
+      if (rc != B200FFT_OK) return rc;
+    }
+    return B200FFT_OK;
+  }
+
   int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) override {
     if (nbatch <= 0) return B200FFT_OK;
+    if (use_fallback) return run_fallback(src, dst, nbatch, stream);
+    if (h_err && *reinterpret_cast<volatile unsigned*>(h_err)) {
+      // a previous launch of this plan gave up waiting for a dependency: its output was invalid and its counters are
+      // stale. Report it once, reset, and leave the statically scheduled kernel for good.
+      *h_err = 0;
+      use_fallback = !fallback.empty();
+      for (auto& kv : per_batch) cudaMemsetAsync(kv.second.d_ctrl, 0, sizeof(unsigned) * (size_t)kv.second.nwords, stream);
+      return fail(B200FFT_ERR_CUDA, "%s: a dependency wait timed out in an earlier launch (its result was invalid)", v->name.c_str());
+    }
     PerBatch* pb = nullptr;
     int rc = prepare(nbatch, &pb);
     if (rc != B200FFT_OK) return rc;
@@ -136,6 +139,7 @@ struct FusedPass : Pass {
     a.nsegs = pb->nsegs;
     a.total_items = pb->total_items;
     a.ctrl = pb->d_ctrl;
+    a.err = d_err;
     for (int p = 0; p < ND_MAX_PHASES; ++p) a.cnt_off[p] = pb->cnt_off[p];
     a.nwords = pb->nwords;
     const unsigned grid = (unsigned)std::min<long long>(pb->total_items, max_grid);
@@ -146,17 +150,13 @@ struct FusedPass : Pass {
         if (!encode_axis_map(&maps[q], dst, geom[q].inner, geom[q].n, geom[q].outer_per_batch * nbatch, geom[q].cw,
                              geom[q].box_rows))
           return fail(B200FFT_ERR_CUDA, "cuTensorMapEncodeTiled failed for phase %d of %s", q, v->name.c_str());
-      cudaEvent_t chain = nullptr;
-      if (fused_serialize() && plan->device >= 0 && plan->device < 64) {
-        FusedChain& fc = fused_chain();
-        std::lock_guard<std::mutex> lock(fc.mu);
-        if (!fc.ev[plan->device]) cudaEventCreateWithFlags(&fc.ev[plan->device], cudaEventDisableTiming);
-        chain = fc.ev[plan->device];
-        if (chain) cudaStreamWaitEvent(stream, chain, 0);  // after the previous statically scheduled kernel
-        v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
-        if (chain) cudaEventRecord(chain, stream);
-      } else {
-        v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
+      const cudaError_t e = v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
+      if (e != cudaSuccess) {
+        // refused (the grid cannot be co-resident on this context: fewer SMs than at plan time, MPS / green-context
+        // partition, cooperative launch unsupported): nothing was launched; run the per-axis kernels from now on
+        cudaGetLastError();
+        use_fallback = true;
+        return run_fallback(src, dst, nbatch, stream);
       }
     } else {
       v->launch(a, grid, v->smem, stream);
@@ -164,6 +164,9 @@ struct FusedPass : Pass {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     B200_CUDA_CHECK(cudaGetLastError());
     return B200FFT_OK;
+  }
+  ~FusedPass() override {
+    if (h_err) cudaFreeHost(h_err);
   }
   std::string describe() const override { return text; }
 };
@@ -357,6 +360,27 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
     return nullptr;
   }
   pass->max_grid = occ * plan.sm_count;
+  if (v.async) {
+    int coop = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, plan.device) != cudaSuccess || !coop) {
+      cudaGetLastError();
+      return nullptr;  // the per-axis kernels run instead
+    }
+  }
+  if (cudaHostAlloc(&pass->h_err, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&pass->d_err, pass->h_err, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (pass->h_err) cudaFreeHost(pass->h_err);
+    pass->h_err = pass->d_err = nullptr;  // no error word: the kernels then only lose the time-out report
+  } else {
+    *pass->h_err = 0;
+  }
+  // schedule + counters for the plan's own batch are built NOW, so that b200fft_exec itself never allocates or
+  // synchronises (graph capture, asynchronous callers); other batch counts (exec_host chunks) are prepared on first use
+  {
+    FusedPass::PerBatch* pb = nullptr;
+    if (pass->prepare(p.batch, &pb) != B200FFT_OK) return nullptr;
+  }
   std::string stages;
   for (int a = 0; a < p.rank; ++a) {
     stages += a ? " | " : "";

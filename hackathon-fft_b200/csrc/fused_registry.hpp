@@ -32,7 +32,7 @@ struct FusedVariant {
   // v2 (fused2.cuh): producer warp + bulk-async staging; threads = consumers + 32
   int default_min_batch = 0;  // > 0: used without B200FFT_FUSED=1 when the batch is at least this (measured wins only)
   bool async = false;
-  void (*launch_async)(const NdArgs&, const CUtensorMap&, const CUtensorMap&, unsigned, size_t, cudaStream_t) = nullptr;
+  cudaError_t (*launch_async)(const NdArgs&, const CUtensorMap&, const CUtensorMap&, unsigned, size_t, cudaStream_t) = nullptr;
   const void* func = nullptr;
 };
 
@@ -45,11 +45,25 @@ struct FusedV {
   }
 };
 
+// The v2 kernel assigns tiles to CTAs statically and lets CTAs wait on counters other CTAs own: every CTA of the grid
+// must be resident at the same time. A cooperative launch is the CUDA guarantee for exactly that (the launch waits until
+// the whole grid fits, and is refused with cudaErrorCooperativeLaunchTooLarge when it never can: MPS / green-context
+// partitions with fewer SMs than the plan saw).
 template <int NT, int MINB, class P0, class P1, class P2>
 struct FusedAsyncV {
-  static void launch(const NdArgs& a, const CUtensorMap& m1, const CUtensorMap& m2, unsigned grid, size_t smem,
-                     cudaStream_t st) {
-    nd_async_kernel<NT, MINB, P0, P1, P2><<<grid, NT + 32, smem, st>>>(a, m1, m2);
+  static cudaError_t launch(const NdArgs& a, const CUtensorMap& m1, const CUtensorMap& m2, unsigned grid, size_t smem,
+                            cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NT + 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, nd_async_kernel<NT, MINB, P0, P1, P2>, a, m1, m2);
   }
 };
 

@@ -52,6 +52,9 @@ struct Pass {
   }
   int axis = -1;
   BufSel src_sel = BUF_OUTPUT, dst_sel = BUF_OUTPUT;
+  // A pass that stands for ALL axes (the fused N-d kernel) carries the per-axis passes of the same plan: they run
+  // in its place when its launch is refused (cooperative launch cannot be satisfied on this context).
+  std::vector<std::unique_ptr<Pass>> fallback;
 };
 
 struct DeviceTwiddles {
@@ -68,6 +71,7 @@ struct b200fft_plan {
   std::vector<b200fft::DeviceTwiddles> tw;  // one per axis (null for skipped axes)
   std::vector<std::unique_ptr<b200fft::Pass>> passes;
   std::vector<void*> owned_device;          // misc device allocations freed at destroy
+  bool building_fallback = false;           // build_passes is collecting the per-axis passes behind a fused pass
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   size_t work_stride = 0;     // workspace bytes per batch item

@@ -26,6 +26,9 @@ struct b200fft_slab {
   unsigned total_items = 0;
   int grid = 148;
   unsigned epoch[2] = {0, 0};
+  unsigned* h_err = nullptr;  // mapped host word: raised by the kernel when a wait for a peer (or a local plane) gave up
+  unsigned* d_err = nullptr;
+  bool poisoned = false;      // sticky: a time-out left the epoch counters of the ranks out of step
   void (*launch)(const SlabArgs&, unsigned, size_t, cudaStream_t) = nullptr;
   const void* func = nullptr;
   std::vector<int> radices;
@@ -33,6 +36,17 @@ struct b200fft_slab {
 };
 
 namespace {
+
+struct DeviceGuard {  // run on the plan's device, give the caller its own device back (like api.cu)
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
 
 template <int N, class RL, int C, int CW, int NT, bool INV>
 void launch_slab(const SlabArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
@@ -69,12 +83,12 @@ extern "C" {
 
 int b200fft_slab_destroy(b200fft_slab* s) {
   if (!s) return B200FFT_OK;
-  int prev = -1;
-  cudaGetDevice(&prev);
-  cudaSetDevice(s->device);
-  for (void* p : {(void*)s->twx, (void*)s->twy, (void*)s->twz, (void*)s->d_segs, (void*)s->d_ctrl})
-    if (p) cudaFree(p);
-  if (prev >= 0) cudaSetDevice(prev);
+  {
+    DeviceGuard guard(s->device);
+    for (void* p : {(void*)s->twx, (void*)s->twy, (void*)s->twz, (void*)s->d_segs, (void*)s->d_ctrl})
+      if (p) cudaFree(p);
+    if (s->h_err) cudaFreeHost(s->h_err);
+  }
   delete s;
   return B200FFT_OK;
 }
@@ -92,7 +106,7 @@ int b200fft_slab_create(b200fft_slab** out, int64_t n, int ranks, int rank, int 
   if (prop.major != 10)
     return fail(B200FFT_ERR_CUDA, "device %d is sm_%d%d; this library only carries sm_100a code (no fallback)", device,
                 prop.major, prop.minor);
-  B200_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard guard(device);  // the caller's current device is restored on every return path
   s->device = device;
   s->ranks = ranks;
   s->rank = rank;
@@ -152,6 +166,14 @@ int b200fft_slab_create(b200fft_slab** out, int64_t n, int ranks, int rank, int 
     return fail(B200FFT_ERR_CUDA, "fused slab kernel does not fit an SM");
   }
   s->grid = occ * prop.multiProcessorCount;
+  if (cudaHostAlloc(&s->h_err, sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess &&
+      cudaHostGetDevicePointer(&s->d_err, s->h_err, 0) == cudaSuccess) {
+    *s->h_err = 0;
+  } else {
+    cudaGetLastError();
+    if (s->h_err) cudaFreeHost(s->h_err);
+    s->h_err = s->d_err = nullptr;
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) {  // tables, schedule and zeroed counters are in place before any exec
     cudaGetLastError();
     b200fft_slab_destroy(s.release());
@@ -181,9 +203,14 @@ size_t b200fft_slab_describe(const b200fft_slab* s, char* buf, size_t cap) {
 int b200fft_slab_exec(b200fft_slab* s, const void* d_in, void* d_work, void* const* peer_recv, int buffer, void* cu_stream) {
   if (!s || !d_in || !d_work || !peer_recv) return fail(B200FFT_ERR_INVALID_ARG, "null slab plan or buffer");
   if (buffer < 0 || buffer > 1) return fail(B200FFT_ERR_INVALID_ARG, "receive buffer index must be 0 or 1");
-  int prev = -1;
-  B200_CUDA_CHECK(cudaGetDevice(&prev));
-  if (prev != s->device) B200_CUDA_CHECK(cudaSetDevice(s->device));
+  if (s->poisoned || (s->h_err && *reinterpret_cast<volatile unsigned*>(s->h_err))) {
+    // Sticky: after a time-out the arrival counters of the ranks no longer agree on the epoch, so every later call
+    // would be wrong too. The caller must destroy the plans, re-zero the receive buffers on every rank and start over.
+    s->poisoned = true;
+    return fail(B200FFT_ERR_CUDA, "slab plan is poisoned: an earlier call timed out waiting for a peer (a rank died or skipped a "
+                                  "call); its result was invalid. Re-zero the receive buffers on every rank and recreate the plans");
+  }
+  DeviceGuard guard(s->device);
   SlabArgs a;
   memset(&a, 0, sizeof a);
   a.in = reinterpret_cast<const float2*>(d_in);
@@ -201,6 +228,7 @@ int b200fft_slab_exec(b200fft_slab* s, const void* d_in, void* d_work, void* con
   a.ranks = s->ranks;
   a.rank = s->rank;
   a.nb = s->nb;
+  a.err = s->d_err;
   a.want = ++s->epoch[buffer] * (unsigned)s->n;  // every rank adds zl per x-block: ranks * zl = n per call
   a.segs = s->d_segs;
   a.total_items = s->total_items;
@@ -212,7 +240,6 @@ int b200fft_slab_exec(b200fft_slab* s, const void* d_in, void* d_work, void* con
   s->launch(a, grid, s->smem, (cudaStream_t)cu_stream);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
-  if (prev != s->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(B200FFT_ERR_CUDA, "slab kernel launch failed: %s", cudaGetErrorString(e));
   return B200FFT_OK;
 }

@@ -30,6 +30,7 @@ struct SlabArgs {
   unsigned* peer_ctr[SLAB_MAX_RANKS];// x-block arrival counters of every rank
   const float2 *twx, *twy, *twz;
   int zl, yl, ranks, rank, nb;       // nb = X / CW x-blocks
+  unsigned* err;                     // mapped HOST word: sticky "a wait timed out" flag read by the next slab_exec
   unsigned want;                     // counter value that means "x-block complete" for this call
   const NdSegment* segs;
   unsigned total_items;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(NT, 2) slab_fused_kernel(const __grid_constant
       __syncthreads();
       if (!s_ready) {
         flush_signal();  // never spin while holding a signal somebody may be waiting for
-        if (threadIdx.x == 0) wait_counter_gpu(a.ctrl + 2 + z, (unsigned)ROW_TILES_PER_PLANE, 64);
+        if (threadIdx.x == 0) wait_counter_gpu(a.ctrl + 2 + z, (unsigned)ROW_TILES_PER_PLANE, 64, a.err);
         __syncthreads();
       }
       const long long base = (long long)z * NY * NX + (long long)b * CW;
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(NT, 2) slab_fused_kernel(const __grid_constant
             __nanosleep(100);
             if (++spins > 20000000u) {
               atomicAdd(a.peer_ctr[a.rank] + a.nb, 1u);
+              if (a.err) atomicExch_system(a.err, 1u);
               break;
             }
           }

@@ -92,7 +92,7 @@ def test_gpu_test_tiers_on_the_golden_vectors(golden, tier):
     """fft/tests.mojo:398-417 runs its vectors once per `_GPUTest` value; here each value forces one kernel tier of
     this library (b200fft.GPUTest) and the plan's description shows the tier really ran."""
     names = {b200fft.GPUTest.BLOCK: ("rows", "cols"), b200fft.GPUTest.WARP: ("rt_", "generic"),
-             b200fft.GPUTest.DEVICE_WIDE: ("fused", "rows", "cols"), b200fft.GPUTest.CLUSTER: ("generic",)}[tier]
+             b200fft.GPUTest.DEVICE_WIDE: ("fused ", "rows", "cols"), b200fft.GPUTest.CLUSTER: ("generic",)}[tier]
     for length, bases in CASES[::3]:
         vs = golden["vectors_1d"][str(length)]
         x = np.array([v["x"] for v in vs], dtype=np.float32)[:, :, None]
@@ -108,7 +108,7 @@ def test_gpu_test_tiers_on_the_golden_vectors(golden, tier):
     text = []
     got = run_gpu(x, tier=tier, describe=text)
     check_vs(got, np.fft.fftn(c2(x), axes=(1, 2, 3)), RTOL_L2_NP, RTOL_MAX_NP)
-    assert ("fused" in text[0]) == (tier == b200fft.GPUTest.DEVICE_WIDE), text[0]
+    assert text[0].startswith("fused ") == (tier == b200fft.GPUTest.DEVICE_WIDE), text[0]
     assert any(n in text[0] for n in names), text[0]
 
 
