@@ -169,13 +169,24 @@ struct FastPass : Pass {
   std::string text;
 
   int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) override {
+    return launch_outer(src, dst, nbatch * view.outer_per_batch, stream);
+  }
+  bool supports_units() const override { return true; }
+  int launch_units(const void* src, void* dst, int64_t nunits, int64_t units_per_batch, cudaStream_t stream) override {
+    if (units_per_batch < 1 || view.outer_per_batch % units_per_batch)
+      return fail(B200FFT_ERR_INVALID_ARG, "%s: %lld outer slabs per batch item do not split into %lld units", text.c_str(),
+                  (long long)view.outer_per_batch, (long long)units_per_batch);
+    return launch_outer(src, dst, nunits * (view.outer_per_batch / units_per_batch), stream);
+  }
+  // `outer` consecutive outer slabs (rows passes: rows) starting at src / dst
+  int launch_outer(const void* src, void* dst, int64_t outer, cudaStream_t stream) {
     if (half != HALF_NONE) {
       HalfArgs a;
       a.in = src;
       a.out = dst;
       a.tw = d_tw;
       a.tw2 = d_tw2;
-      a.nrows = nbatch * view.outer_per_batch;
+      a.nrows = outer;
       a.scale = scale;
       const long long grid = (a.nrows + v->tile - 1) / v->tile;
       if (grid <= 0) return B200FFT_OK;
@@ -188,7 +199,7 @@ struct FastPass : Pass {
       a.in = src;
       a.out = reinterpret_cast<float2*>(dst);
       a.tw = d_tw;
-      a.nrows = nbatch * view.outer_per_batch;
+      a.nrows = outer;
       a.scale = scale;
       a.do_scale = do_scale;
       const long long grid = (a.nrows + v->tile - 1) / v->tile;
@@ -196,7 +207,6 @@ struct FastPass : Pass {
       if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many row tiles");
       v->launch_rows(inverse, real_in, a, (unsigned)grid, v->smem, stream);
     } else if (v->kind == COLS_TMA) {
-      const long long outer = nbatch * view.outer_per_batch;
       CUtensorMap mi, mo;
       if (!encode_axis_map(&mi, src, view.inner, view.n, outer, v->tile, v->box_rows) ||
           !encode_axis_map(&mo, dst, view.inner, view.n, outer, v->tile, v->box_rows))
@@ -219,7 +229,7 @@ struct FastPass : Pass {
       a.tiles_per_outer = (int)((view.inner + v->tile - 1) / v->tile);
       a.scale = scale;
       a.do_scale = do_scale;
-      const long long grid = nbatch * view.outer_per_batch * a.tiles_per_outer;
+      const long long grid = outer * a.tiles_per_outer;
       if (grid <= 0) return B200FFT_OK;
       if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many column tiles");
       v->launch_cols(inverse, real_in, a, (unsigned)grid, v->smem, stream);

@@ -31,6 +31,7 @@ constexpr int ND_MAX_PHASES = 3;
 struct NdPhase {
   const float2* tw;              // stage twiddles of the (first) axis of this phase
   const float2* tw2;             // second table: y axis of a plane phase / W_n^k of the R2C unpack
+  const float2* tw3;             // R2C plane phase: W_n^k of the unpack (tw = x stages, tw2 = y stages)
   long long inner;               // cols: element stride along the axis
   long long units_per_transform; // rows / r2c: rows per transform
   int tiles_per_outer;           // cols: tiles per outer slab
@@ -80,7 +81,7 @@ __device__ __forceinline__ void wait_counter_gpu(const unsigned* cnt, unsigned w
 }
 
 // ---- phases: the tile bodies of fast.cuh as device functions --------------------------------------
-enum NdKind { ND_NONE = 0, ND_ROWS = 1, ND_COLS = 2, ND_R2C = 3, ND_PLANE = 4 };
+enum NdKind { ND_NONE = 0, ND_ROWS = 1, ND_COLS = 2, ND_R2C = 3, ND_PLANE = 4, ND_R2C_PLANE = 5 };
 
 struct NdNone {
   using RL = Radices<1>;

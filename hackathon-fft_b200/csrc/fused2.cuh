@@ -224,6 +224,69 @@ struct APlane {
   }
 };
 
+// Half-spectrum (y, x) plane: NY real rows of n = 2H points -> the plane's NY x (H + 1) block of the half spectrum,
+// x AND y transformed, in one tile. The real plane (NY * n floats, contiguous) arrives by one bulk copy; the rows run as
+// H-point complex transforms (the same bytes viewed as z[m] = x[2m] + i x[2m+1]), the Hermitian unpack writes the
+// H + 1 bins of every row into a shared-memory plane, the y pass runs on that plane over H + 1 (odd!) columns, and
+// its last stage stores the finished block, which is contiguous in the output. The ragged H + 1 extent that no TMA
+// box or 16-column tile fits (33 bins for n = 64) never reaches global memory half-done: the middle pass of the
+// per-axis plan (2 full tiles + 1 column, profiles/r1_r2c.md) disappears, and HBM sees one read + one write for two
+// axes. The strided z phase that follows has inner = NY * (H + 1), a multiple of NY: whole TMA tiles again.
+// Shared memory: region R1 = x exchange, later the unpacked plane; region R2 = x result Z, later the y exchange.
+template <int NY, int H, class RLY_, class RLX_>
+struct AR2CPlane {
+  using RL = RLX_;
+  using RLY = RLY_;
+  static constexpr bool none = false;
+  static constexpr int kind = ND_R2C_PLANE, n = 2 * H, n2 = NY, tile = 1;
+  static constexpr bool inverse = false, real = true;
+  static constexpr int HB = H + 1;
+  static_assert(RLX_::count == 2 && RLY_::count == 2, "r2c plane tiles: two super-stages per axis");
+  static constexpr int EXR = max_exchange_elems<RLX_, NY, RowLayoutN<H>::template type>();
+  static constexpr int R1 = EXR > NY * HB ? EXR : NY * HB;
+  static constexpr int R2 = NY * HB;
+  static constexpr size_t in_bytes = (size_t)NY * H * 8;
+  static constexpr size_t ex_bytes = sizeof(float2) * (size_t)(R1 + R2);
+  static constexpr int tw_elems = RLX_::tw_total(), tw2_elems = RLY_::tw_total();
+  static __device__ __forceinline__ void load(const NdPhase&, const CUtensorMap*, const void* src_t, long long, int tile,
+                                              void* in_buf, uint64_t* full) {
+    tma::mbar_arrive_expect_tx(full, (uint32_t)in_bytes);
+    tma::load_1d(in_buf, reinterpret_cast<const float2*>(src_t) + (long long)tile * NY * H, (uint32_t)in_bytes, full);
+  }
+  template <int NT, class Rel>
+  static __device__ __forceinline__ void run(const NdPhase& p, const float2* tw, const float2* tw2, const void* in_buf,
+                                             float2* dst_t, int tile, float2* ex, Rel release) {
+    float2* r1 = ex;
+    float2* r2 = ex + R1;
+    // x, stage 0: staged real rows (as H complex) -> r1 (padded rows)
+    using LX = typename RowLayoutN<H>::template type<RLX_::r[0], 1>;
+    run_stage<RLX_::r[0], 1, H, NY, 1, NT, false, true>(StagedRows<H, false>{in_buf}, SmemDst<LX>{r1}, tw, 1.f, false);
+    tile_sync<NT, true>();
+    release();  // the staging slot is free for the next tile's copy
+    // x, stage 1: r1 -> Z = r2, dense [row][k]
+    run_stage<RLX_::r[1], RLX_::r[0], H, NY, 1, NT, false, true>(SmemSrc<LX>{r1}, SmemDst<PlaneLayout<H>>{r2},
+                                                                 tw + RLX_::tw_offset(1), 1.f, false);
+    tile_sync<NT, true>();
+    // Hermitian unpack: X[k] = (Z[k] + conj(Z[H-k]))/2 - (i/2) W_n^k (Z[k] - conj(Z[H-k])), k = 0..H -> r1 as [row][HB]
+    for (int idx = threadIdx.x; idx < NY * HB; idx += NT) {
+      const int o = idx / HB, k = idx - o * HB;
+      const float2 zk = r2[o * H + (k == H ? 0 : k)];
+      float2 zm = r2[o * H + (k == 0 ? 0 : H - k)];
+      zm.y = -zm.y;
+      const float2 s = make_float2(zk.x + zm.x, zk.y + zm.y), d = make_float2(zk.x - zm.x, zk.y - zm.y);
+      const float2 t = cmulf(d, __ldg(&p.tw3[k]));
+      r1[idx] = make_float2(0.5f * (s.x + t.y), 0.5f * (s.y - t.x));
+    }
+    tile_sync<NT, true>();
+    // y over the HB columns of the plane: r1 -> r2 -> global (the plane's block of the half spectrum is contiguous)
+    using LY = DenseLayout<NY, HB>;
+    run_stage<RLY_::r[0], 1, NY, 1, HB, NT, false, true>(SmemSrc<LY>{r1}, SmemDst<LY>{r2}, tw2, 1.f, false);
+    tile_sync<NT, true>();
+    GlobalDst d{dst_t + (long long)tile * NY * HB, 0, HB, 1, HB};
+    run_stage<RLY_::r[1], RLY_::r[0], NY, 1, HB, NT, false, true>(SmemSrc<LY>{r2}, d, tw2 + RLY_::tw_offset(1), 1.f, false);
+  }
+};
+
 // ---- kernel ------------------------------------------------------------------------------------------------
 struct NdLocate {
   int seg;

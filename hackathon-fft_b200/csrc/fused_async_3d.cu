@@ -18,8 +18,17 @@ static void reg3d_async() {
   reg_fused_async<256, 2, ARows<512, R32x16, 8, INV, false>, ACols<512, R32x16, 8, INV>, ACols<512, R32x16, 8, INV>>(
       {512, 512, 512}, 0);
 }
+// half-spectrum R2C: (y, x) planes with the Hermitian unpack and the y pass in shared memory, then the strided z phase
+// over inner = NY * (n/2 + 1) (whole 64-column tiles)
+static void reg3d_async_r2c() {
+  using R8x8 = Radices<8, 8>;
+  using R8x4 = Radices<8, 4>;
+  reg_fused_async<288, 2, AR2CPlane<64, 32, R8x8, R8x4>, ACols<64, R8x8, 32, false>>({64, 64, 64}, 2, "z32", 1);
+  reg_fused_async<288, 2, AR2CPlane<64, 32, R8x8, R8x4>, ACols<64, R8x8, 64, false>>({64, 64, 64}, 2, "z64");
+}
 void register_fused_async_3d() {
   reg3d_async<false>();
   reg3d_async<true>();
+  reg3d_async_r2c();
 }
 }  // namespace b200fft

@@ -150,7 +150,10 @@ struct FusedPass : Pass {
         if (!encode_axis_map(&maps[q], dst, geom[q].inner, geom[q].n, geom[q].outer_per_batch * nbatch, geom[q].cw,
                              geom[q].box_rows))
           return fail(B200FFT_ERR_CUDA, "cuTensorMapEncodeTiled failed for phase %d of %s", q, v->name.c_str());
-      const cudaError_t e = v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
+      // B200FFT_TEST_REFUSE_COOP=1 (tests): behave as if the driver had refused the cooperative launch
+      const char* refuse = getenv("B200FFT_TEST_REFUSE_COOP");
+      const cudaError_t e = (refuse && atoi(refuse)) ? cudaErrorCooperativeLaunchTooLarge
+                                                     : v->launch_async(a, maps[1], maps[2], grid, v->smem, stream);
       if (e != cudaSuccess) {
         // refused (the grid cannot be co-resident on this context: fewer SMs than at plan time, MPS / green-context
         // partition, cooperative launch unsupported): nothing was launched; run the per-axis kernels from now on
@@ -219,7 +222,7 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
       int next_axis = last;
       for (int q = 0; q < v.nphases && ok; ++q) {
         const FusedPhaseInfo& ph = v.ph[q];
-        if (q == 0 && ph.kind == ND_PLANE) { axes.push_back(last); next_axis = last - 2; }
+        if (q == 0 && (ph.kind == ND_PLANE || ph.kind == ND_R2C_PLANE)) { axes.push_back(last); next_axis = last - 2; }
         else if (q == 0 && (ph.kind == ND_ROWS || ph.kind == ND_R2C)) { axes.push_back(last); next_axis = last - 1; }
         else if (q > 0 && ph.kind == ND_COLS && next_axis >= 0) { axes.push_back(next_axis); --next_axis; }
         else ok = false;
@@ -229,10 +232,11 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
       for (int q = 0; q < v.nphases && ok; ++q) {
         const FusedPhaseInfo& ph = v.ph[q];
         const int a = axes[q];
-        if (ph.kind == ND_R2C) {
+        if (ph.kind == ND_R2C || ph.kind == ND_R2C_PLANE) {
           bool any = false;
           for (const auto& o : drop_factor_two(p.axes[a].ordered)) any = any || can_group(o, ph.radices);
           ok = any && dims[a] == ph.n;
+          if (ok && ph.kind == ND_R2C_PLANE) ok = a >= 1 && dims[a - 1] == ph.n2 && can_group(p.axes[a - 1].ordered, ph.radices2);
         } else {
           ok = dims[a] == ph.n && can_group(p.axes[a].ordered, ph.radices);
           if (ok && ph.kind == ND_PLANE) ok = dims[a - 1] == ph.n2 && can_group(p.axes[a - 1].ordered, ph.radices2);
@@ -301,12 +305,13 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
       P.tiles_per_outer = 1;
       if (ph.kind == ND_R2C && !upload(build_half_twiddles(dims[last], false), &P.tw2)) return nullptr;
       tile_bytes = (long long)ph.tile * cdims[last] * 8;
-    } else if (ph.kind == ND_PLANE) {
+    } else if (ph.kind == ND_PLANE || ph.kind == ND_R2C_PLANE) {
       P.units_per_transform = prod(dims, 0, last - 1);
       P.tiles_per_transform = (int)P.units_per_transform;
       P.tiles_per_outer = 1;
       if (!upload(build_twiddles(ph.radices2, inv), &P.tw2)) return nullptr;
-      tile_bytes = dims[last] * dims[last - 1] * 8;
+      if (ph.kind == ND_R2C_PLANE && !upload(build_half_twiddles(dims[last], false), &P.tw3)) return nullptr;
+      tile_bytes = cdims[last] * dims[last - 1] * 8;
     } else {  // ND_COLS on axis a
       P.inner = prod(cdims, a + 1, cdims.size());
       P.tiles_per_outer = (int)((P.inner + ph.tile - 1) / ph.tile);

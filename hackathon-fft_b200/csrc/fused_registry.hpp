@@ -73,7 +73,13 @@ FusedPhaseInfo fused_phase_info() {
   i.kind = P::kind;
   i.n = P::n;
   i.tile = P::tile;
-  if constexpr (P::kind == ND_PLANE) {
+  if constexpr (P::kind == ND_R2C_PLANE) {
+    i.n2 = P::n2;
+    i.radices = radix_vec<typename P::RL>();
+    i.radices2 = radix_vec<typename P::RLY>();
+    i.text = "r2cplane" + std::to_string(P::n2) + "x" + std::to_string(P::n) + "(" + radix_name(i.radices2) + ";2;" +
+             radix_name(i.radices) + ")";
+  } else if constexpr (P::kind == ND_PLANE) {
     i.n2 = P::n2;
     i.radices = radix_vec<typename P::RL>();
     i.radices2 = radix_vec<typename P::RLY>();

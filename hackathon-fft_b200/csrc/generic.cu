@@ -155,10 +155,19 @@ struct GenericPass : Pass {
   std::string text;
 
   int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) override {
+    return launch_outer(src, dst, nbatch * outer_per_batch, stream);
+  }
+  bool supports_units() const override { return true; }
+  int launch_units(const void* src, void* dst, int64_t nunits, int64_t units_per_batch, cudaStream_t stream) override {
+    if (units_per_batch < 1 || outer_per_batch % units_per_batch)
+      return fail(B200FFT_ERR_INVALID_ARG, "%s: outer slabs do not split into %lld units", text.c_str(), (long long)units_per_batch);
+    return launch_outer(src, dst, nunits * (outer_per_batch / units_per_batch), stream);
+  }
+  int launch_outer(const void* src, void* dst, long long outer, cudaStream_t stream) {
     GenParams p = base;
     p.src = src;
     p.dst = dst;
-    p.outer = nbatch * outer_per_batch;
+    p.outer = outer;
     if (p.row) {
       p.tiles_per_outer = 1;
       p.ntiles = (p.outer + p.C - 1) / p.C;

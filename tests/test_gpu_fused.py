@@ -65,6 +65,10 @@ CASES = [
     ((3, 640, 480), True, "c2c", "ndA640"),
     ((5, 640, 480), False, "real", "ndA640"),
     ((1, 640, 480), False, "c2c", "ndA640"),
+    # half-spectrum 3-D: (y, x) planes with unpack + y pass in shared memory (AR2CPlane), then the strided z phase
+    ((5, 64, 64, 64), False, "half", "r2cplane64x64(8x8;2;8x4)_z32"),
+    ((37, 64, 64, 64), False, "half", "r2cplane64x64(8x8;2;8x4)_z32"),
+    ((3, 64, 64, 64), False, "half", "r2cplane64x64(8x8;2;8x4)_z64"),
 ]
 
 
@@ -144,9 +148,53 @@ def test_fused_through_exec_host():
     _check(h_out.cuda(), want)
 
 
+def test_fused_exec_is_graph_capturable():
+    """b200fft_exec of a fused plan neither allocates nor synchronises (the schedule is built at plan creation, the
+    launch is cooperative, no event chain): it can be captured into a CUDA graph and replayed."""
+    import torch
+    x = torch.randn((8, 64, 64, 64, 2), device="cuda")
+    out = torch.full_like(x, float("nan"))
+    plan = b200fft.plan_fft("float32", "float32", x.shape, x.shape)
+    assert plan.describe().startswith("fused ndA")
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g, stream=st):
+            plan.exec(out, x, st.cuda_stream)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    _check(out, _ref(x))
+
+
+def test_refused_cooperative_launch_falls_back_to_per_axis_passes(monkeypatch):
+    """ADVICE r1: a statically scheduled grid that cannot be co-resident must not be launched. The launch is cooperative;
+    when the driver refuses it (simulated here) the plan's per-axis passes run instead and the result is the same."""
+    import torch
+    x = torch.randn((4, 64, 64, 64, 2), device="cuda")
+    plan = b200fft.plan_fft("float32", "float32", x.shape, x.shape)
+    assert plan.describe().startswith("fused ndA")
+    good = torch.empty_like(x)
+    b200fft.fft(good, x, plan=plan)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("B200FFT_TEST_REFUSE_COOP", "1")
+    before = b200fft.launch_count()
+    out = torch.full_like(x, float("nan"))
+    b200fft.fft(out, x, plan=plan)
+    torch.cuda.synchronize()
+    assert b200fft.launch_count() - before == 3          # three per-axis kernels, not one fused launch
+    _check(out, _ref(x))
+    assert float((out - good).norm() / good.norm()) < 1e-6
+    monkeypatch.delenv("B200FFT_TEST_REFUSE_COOP")
+    b200fft.fft(out, x, plan=plan)                       # the plan stays on the fallback once refused
+    torch.cuda.synchronize()
+    _check(out, _ref(x))
+
+
 def test_two_fused_plans_on_two_streams():
-    """Statically scheduled persistent kernels are chained device-wide, so two plans launched back to back on
-    different streams cannot starve each other of SMs (each grid is sized to the whole device)."""
+    """Statically scheduled persistent kernels are launched cooperatively: each launch waits until its whole grid can be
+    resident, so two plans launched back to back on different streams cannot starve each other of SMs."""
     import torch
     xs = [torch.randn((40, 64, 64, 64, 2), device="cuda") for _ in range(2)]
     outs = [torch.empty_like(x) for x in xs]
