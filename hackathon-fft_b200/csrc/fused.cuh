@@ -31,7 +31,6 @@ constexpr int ND_MAX_PHASES = 3;
 struct NdPhase {
   const float2* tw;              // stage twiddles of the (first) axis of this phase
   const float2* tw2;             // second table: y axis of a plane phase / W_n^k of the R2C unpack
-  const float2* tw3;             // R2C plane phase: W_n^k of the unpack (tw = x stages, tw2 = y stages)
   long long inner;               // cols: element stride along the axis
   long long units_per_transform; // rows / r2c: rows per transform
   int tiles_per_outer;           // cols: tiles per outer slab
@@ -57,6 +56,7 @@ struct NdArgs {
   unsigned* err;                  // mapped HOST word: set to 1 when a dependency wait gave up (checked by the next exec)
   int cnt_off[ND_MAX_PHASES];     // offset of each phase's counters inside ctrl
   int nwords;                     // words to clear at the end (header + counters)
+  int prefetch_ahead;             // v2: L2-prefetch the input of the phase-0 tile this many of the CTA's own items ahead (0 = off)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {

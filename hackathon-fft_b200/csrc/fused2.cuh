@@ -18,7 +18,7 @@
 
 namespace b200fft {
 
-constexpr int ND_RING = 2;  // input ring depth
+constexpr int ND_RING = 2;  // default input ring depth (a kernel template parameter: 1 trades look-ahead for CTAs per SM)
 
 struct NdItem {  // ring slot descriptor, written by the producer before it arrives on full[slot]
   int phase;     // -1 = no more work
@@ -36,6 +36,10 @@ __device__ __forceinline__ void load_1d(void* smem_dst, const void* gsrc, uint32
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bring [gsrc, gsrc + bytes) into L2 ahead of the copy that will stage it (no shared memory, no completion to wait for)
+__device__ __forceinline__ void prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 // order earlier generic-proxy accesses (the acquire that observed other SMs' st.global) before later
 // async-proxy reads of global memory (the bulk copies)
@@ -63,6 +67,7 @@ struct ANone {
   static constexpr int tw_elems = 0, tw2_elems = 0;
   static __device__ __forceinline__ void load(const NdPhase&, const CUtensorMap*, const void*, long long, int, void*,
                                               uint64_t*) {}
+  static __device__ __forceinline__ void prefetch(const NdPhase&, const void*, int) {}
   template <int NT, class Rel>
   static __device__ __forceinline__ void run(const NdPhase&, const float2*, const float2*, const void*, float2*, int,
                                              float2*, Rel) {}
@@ -85,6 +90,11 @@ struct ARows {
     const uint32_t bytes = (uint32_t)valid * N * ELEM;
     tma::mbar_arrive_expect_tx(full, bytes);
     tma::load_1d(in_buf, reinterpret_cast<const char*>(src_t) + row0 * N * ELEM, bytes, full);
+  }
+  static __device__ __forceinline__ void prefetch(const NdPhase& p, const void* src_t, int tile) {
+    const long long row0 = (long long)tile * C;
+    const int valid = (int)min((long long)C, p.units_per_transform - row0);
+    tma::prefetch_l2(reinterpret_cast<const char*>(src_t) + row0 * N * ELEM, (uint32_t)valid * N * ELEM);
   }
   template <int NT, class Rel>
   static __device__ __forceinline__ void run(const NdPhase& p, const float2* tw, const float2*, const void* in_buf,
@@ -130,6 +140,7 @@ struct ACols {
     for (int b = 0; b < N / BR; ++b)
       tma::load_3d(reinterpret_cast<float2*>(in_buf) + b * BR * CW, map, c0, b * BR, outer, full);
   }
+  static __device__ __forceinline__ void prefetch(const NdPhase&, const void*, int) {}  // reads the L2-resident intermediate
   template <int NT, class Rel>
   static __device__ __forceinline__ void run(const NdPhase& p, const float2* tw, const float2*, const void* in_buf,
                                              float2* dst_t, int tile, float2* ex, Rel release) {
@@ -172,6 +183,11 @@ struct AR2C {
     tma::mbar_arrive_expect_tx(full, bytes);
     tma::load_1d(in_buf, reinterpret_cast<const char*>(src_t) + row0 * H * 8, bytes, full);
   }
+  static __device__ __forceinline__ void prefetch(const NdPhase& p, const void* src_t, int tile) {
+    const long long row0 = (long long)tile * C;
+    const int valid = (int)min((long long)C, p.units_per_transform - row0);
+    tma::prefetch_l2(reinterpret_cast<const char*>(src_t) + row0 * H * 8, (uint32_t)valid * H * 8);
+  }
   template <int NT, class Rel>
   static __device__ __forceinline__ void run(const NdPhase& p, const float2* tw, const float2*, const void* in_buf,
                                              float2* dst_t, int tile, float2* ex, Rel release) {
@@ -202,6 +218,9 @@ struct APlane {
     tma::mbar_arrive_expect_tx(full, (uint32_t)in_bytes);
     tma::load_1d(in_buf, reinterpret_cast<const float2*>(src_t) + (long long)tile * NY * NX, (uint32_t)in_bytes, full);
   }
+  static __device__ __forceinline__ void prefetch(const NdPhase&, const void* src_t, int tile) {
+    tma::prefetch_l2(reinterpret_cast<const float2*>(src_t) + (long long)tile * NY * NX, (uint32_t)in_bytes);
+  }
   template <int NT, class Rel>
   static __device__ __forceinline__ void run(const NdPhase& p, const float2* tw, const float2* tw2, const void* in_buf,
                                              float2* dst_t, int tile, float2* ex, Rel release) {
@@ -226,14 +245,32 @@ struct APlane {
 
 // Half-spectrum (y, x) plane: NY real rows of n = 2H points -> the plane's NY x (H + 1) block of the half spectrum,
 // x AND y transformed, in one tile. The real plane (NY * n floats, contiguous) arrives by one bulk copy; the rows run as
-// H-point complex transforms (the same bytes viewed as z[m] = x[2m] + i x[2m+1]), the Hermitian unpack writes the
-// H + 1 bins of every row into a shared-memory plane, the y pass runs on that plane over H + 1 (odd!) columns, and
-// its last stage stores the finished block, which is contiguous in the output. The ragged H + 1 extent that no TMA
-// box or 16-column tile fits (33 bins for n = 64) never reaches global memory half-done: the middle pass of the
-// per-axis plan (2 full tiles + 1 column, profiles/r1_r2c.md) disappears, and HBM sees one read + one write for two
-// axes. The strided z phase that follows has inner = NY * (H + 1), a multiple of NY: whole TMA tiles again.
-// Shared memory: region R1 = x exchange, later the unpacked plane; region R2 = x result Z, later the y exchange.
-template <int NY, int H, class RLY_, class RLX_>
+// H-point complex transforms (the same bytes viewed as z[m] = x[2m] + i x[2m+1]) whose result Z stays in shared memory;
+// the y pass then runs over the H + 1 (odd!) bins of every row, its stage 0 forming each bin on the fly with the
+// Hermitian unpack X[k] = (Z[k] + conj(Z[H-k]))/2 - (i/2) W_n^k (Z[k] - conj(Z[H-k])), and its last stage stores the
+// finished block, which is contiguous in the output. The ragged H + 1 extent that no TMA box or 16-column tile fits
+// (33 bins for n = 64) never reaches global memory half-done: the middle pass of the per-axis plan (2 full tiles + 1
+// column, profiles/r1_r2c.md) disappears, and HBM sees one read + one write for two axes. The strided z phase that
+// follows has inner = NY * (H + 1), a multiple of NY: whole TMA tiles again.
+// Shared memory: region R1 = x exchange, later the y exchange; region R2 = Z. The phase's twiddle table is
+// [x stage twiddles | W_n^k, k = 0..H] (one table, staged once per CTA), tw2 = the y stage twiddles.
+template <int H>
+struct UnpackSrc {  // bin c of row i from Z[i][0..H)
+  const float2* z;
+  const float2* w;  // W_n^k in shared memory
+  __device__ __forceinline__ float2 load(int, int i, int c) const {
+    const float2 zk = z[i * H + (c == H ? 0 : c)];
+    float2 zm = z[i * H + (c == 0 ? 0 : H - c)];
+    zm.y = -zm.y;
+    const float2 s = make_float2(zk.x + zm.x, zk.y + zm.y), d = make_float2(zk.x - zm.x, zk.y - zm.y);
+    const float2 t = cmulf(d, tw_load<true>(w, c));
+    return make_float2(0.5f * (s.x + t.y), 0.5f * (s.y - t.x));
+  }
+};
+
+// ZSLOT: the x result Z is written back into the staging slot (the real plane it replaces has the same size), so the
+// exchange area is R1 only and more CTAs fit an SM; the slot is then released after the y pass's stage 0.
+template <int NY, int H, class RLY_, class RLX_, bool ZSLOT = false>
 struct AR2CPlane {
   using RL = RLX_;
   using RLY = RLY_;
@@ -244,46 +281,41 @@ struct AR2CPlane {
   static_assert(RLX_::count == 2 && RLY_::count == 2, "r2c plane tiles: two super-stages per axis");
   static constexpr int EXR = max_exchange_elems<RLX_, NY, RowLayoutN<H>::template type>();
   static constexpr int R1 = EXR > NY * HB ? EXR : NY * HB;
-  static constexpr int R2 = NY * HB;
+  static constexpr int R2 = ZSLOT ? 0 : NY * H;
   static constexpr size_t in_bytes = (size_t)NY * H * 8;
   static constexpr size_t ex_bytes = sizeof(float2) * (size_t)(R1 + R2);
-  static constexpr int tw_elems = RLX_::tw_total(), tw2_elems = RLY_::tw_total();
+  static constexpr int tw_elems = RLX_::tw_total() + HB, tw2_elems = RLY_::tw_total();
   static __device__ __forceinline__ void load(const NdPhase&, const CUtensorMap*, const void* src_t, long long, int tile,
                                               void* in_buf, uint64_t* full) {
     tma::mbar_arrive_expect_tx(full, (uint32_t)in_bytes);
     tma::load_1d(in_buf, reinterpret_cast<const float2*>(src_t) + (long long)tile * NY * H, (uint32_t)in_bytes, full);
   }
+  static __device__ __forceinline__ void prefetch(const NdPhase&, const void* src_t, int tile) {
+    tma::prefetch_l2(reinterpret_cast<const float2*>(src_t) + (long long)tile * NY * H, (uint32_t)in_bytes);
+  }
   template <int NT, class Rel>
   static __device__ __forceinline__ void run(const NdPhase& p, const float2* tw, const float2* tw2, const void* in_buf,
                                              float2* dst_t, int tile, float2* ex, Rel release) {
     float2* r1 = ex;
-    float2* r2 = ex + R1;
+    float2* r2 = ZSLOT ? reinterpret_cast<float2*>(const_cast<void*>(in_buf)) : ex + R1;
     // x, stage 0: staged real rows (as H complex) -> r1 (padded rows)
     using LX = typename RowLayoutN<H>::template type<RLX_::r[0], 1>;
     run_stage<RLX_::r[0], 1, H, NY, 1, NT, false, true>(StagedRows<H, false>{in_buf}, SmemDst<LX>{r1}, tw, 1.f, false);
     tile_sync<NT, true>();
-    release();  // the staging slot is free for the next tile's copy
+    if constexpr (!ZSLOT) release();  // the staging slot is free for the next tile's copy
     // x, stage 1: r1 -> Z = r2, dense [row][k]
     run_stage<RLX_::r[1], RLX_::r[0], H, NY, 1, NT, false, true>(SmemSrc<LX>{r1}, SmemDst<PlaneLayout<H>>{r2},
                                                                  tw + RLX_::tw_offset(1), 1.f, false);
     tile_sync<NT, true>();
-    // Hermitian unpack: X[k] = (Z[k] + conj(Z[H-k]))/2 - (i/2) W_n^k (Z[k] - conj(Z[H-k])), k = 0..H -> r1 as [row][HB]
-    for (int idx = threadIdx.x; idx < NY * HB; idx += NT) {
-      const int o = idx / HB, k = idx - o * HB;
-      const float2 zk = r2[o * H + (k == H ? 0 : k)];
-      float2 zm = r2[o * H + (k == 0 ? 0 : H - k)];
-      zm.y = -zm.y;
-      const float2 s = make_float2(zk.x + zm.x, zk.y + zm.y), d = make_float2(zk.x - zm.x, zk.y - zm.y);
-      const float2 t = cmulf(d, __ldg(&p.tw3[k]));
-      r1[idx] = make_float2(0.5f * (s.x + t.y), 0.5f * (s.y - t.x));
-    }
-    tile_sync<NT, true>();
-    // y over the HB columns of the plane: r1 -> r2 -> global (the plane's block of the half spectrum is contiguous)
+    // y over the HB bins of every row, unpacked on the fly: Z -> r1 -> global (the plane's block is contiguous)
     using LY = DenseLayout<NY, HB>;
-    run_stage<RLY_::r[0], 1, NY, 1, HB, NT, false, true>(SmemSrc<LY>{r1}, SmemDst<LY>{r2}, tw2, 1.f, false);
+    run_stage<RLY_::r[0], 1, NY, 1, HB, NT, false, true>(UnpackSrc<H>{r2, tw + RLX_::tw_total()}, SmemDst<LY>{r1}, tw2, 1.f,
+                                                         false);
     tile_sync<NT, true>();
+    if constexpr (ZSLOT) release();
     GlobalDst d{dst_t + (long long)tile * NY * HB, 0, HB, 1, HB};
-    run_stage<RLY_::r[1], RLY_::r[0], NY, 1, HB, NT, false, true>(SmemSrc<LY>{r2}, d, tw2 + RLY_::tw_offset(1), 1.f, false);
+    run_stage<RLY_::r[1], RLY_::r[0], NY, 1, HB, NT, false, true>(SmemSrc<LY>{r1}, d, tw2 + RLY_::tw_offset(1), 1.f, false);
+    (void)p;
   }
 };
 
@@ -359,13 +391,13 @@ constexpr size_t nd_async_in_bytes() {
   m = P2::in_bytes > m ? P2::in_bytes : m;
   return (m + 127) / 128 * 128;
 }
-template <class P0, class P1, class P2>
+template <class P0, class P1, class P2, int RING = ND_RING>
 constexpr size_t nd_async_smem() {
   size_t e = P0::ex_bytes;
   e = P1::ex_bytes > e ? P1::ex_bytes : e;
   e = P2::ex_bytes > e ? P2::ex_bytes : e;
   const size_t tw = sizeof(float2) * (size_t)(P0::tw_elems + P0::tw2_elems + P1::tw_elems + P2::tw_elems);
-  return ND_RING * nd_async_in_bytes<P0, P1, P2>() + (e + 15) / 16 * 16 + tw + 128;  // +128: manual ring alignment
+  return RING * nd_async_in_bytes<P0, P1, P2>() + (e + 15) / 16 * 16 + tw + 128;  // +128: manual ring alignment
 }
 template <class P0, class P1, class P2>
 constexpr size_t nd_async_ex_bytes() {
@@ -376,7 +408,7 @@ constexpr size_t nd_async_ex_bytes() {
 }
 
 // block = NT consumer threads + one producer warp
-template <int NT, int MINB, class P0, class P1, class P2>
+template <int NT, int MINB, class P0, class P1, class P2, int RING = ND_RING>
 __global__ void __launch_bounds__(NT + 32, MINB)
     nd_async_kernel(const __grid_constant__ NdArgs a, const __grid_constant__ CUtensorMap map1,
                     const __grid_constant__ CUtensorMap map2) {
@@ -384,15 +416,15 @@ __global__ void __launch_bounds__(NT + 32, MINB)
   // plain pointer arithmetic so the compiler keeps them in the shared address space (LDS/STS, not generic LD/ST:
   // the first version aligned through uintptr_t and paid 16 % of its stall samples on generic loads)
   extern __shared__ __align__(128) unsigned char smem_async[];
-  __shared__ __align__(8) uint64_t full[ND_RING];
-  __shared__ __align__(8) uint64_t empty[ND_RING];
-  __shared__ NdItem ring[ND_RING];
+  __shared__ __align__(8) uint64_t full[RING];
+  __shared__ __align__(8) uint64_t empty[RING];
+  __shared__ NdItem ring[RING];
   __shared__ int s_last;
   constexpr size_t IN = nd_async_in_bytes<P0, P1, P2>();
   unsigned char* base = smem_async;
-  float2* ex = reinterpret_cast<float2*>(base + ND_RING * IN);
+  float2* ex = reinterpret_cast<float2*>(base + RING * IN);
   // stage twiddle tables, copied once per CTA: every later twiddle read is an LDS
-  float2* tw0 = reinterpret_cast<float2*>(base + ND_RING * IN + nd_async_ex_bytes<P0, P1, P2>());
+  float2* tw0 = reinterpret_cast<float2*>(base + RING * IN + nd_async_ex_bytes<P0, P1, P2>());
   float2* tw0b = tw0 + P0::tw_elems;
   float2* tw1 = tw0b + P0::tw2_elems;
   float2* tw2s = tw1 + P1::tw_elems;
@@ -403,7 +435,7 @@ __global__ void __launch_bounds__(NT + 32, MINB)
     for (int i = threadIdx.x; i < P2::tw_elems; i += NT + 32) tw2s[i] = a.ph[2].tw[i];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < ND_RING; ++i) {
+    for (int i = 0; i < RING; ++i) {
       tma::mbar_init(&full[i], 1);   // the producer's arrive.expect_tx (+ the copies' bytes)
       tma::mbar_init(&empty[i], 1);  // consumer thread 0 after the stage-0 barrier
     }
@@ -439,8 +471,8 @@ __global__ void __launch_bounds__(NT + 32, MINB)
       resolve(item, &rn);
       for (unsigned k = 0;; ++k) {
         r = rn;
-        const int slot = k % ND_RING;
-        if (k >= ND_RING) tma::mbar_wait(&empty[slot], ((k / ND_RING) - 1) & 1);
+        const int slot = k % RING;
+        if (k >= RING) tma::mbar_wait(&empty[slot], ((k / RING) - 1) & 1);
         if (r.phase < 0) {
           ring[slot].phase = -1;
           tma::mbar_arrive(&full[slot]);
@@ -454,6 +486,22 @@ __global__ void __launch_bounds__(NT + 32, MINB)
         else if constexpr (!P2::none) nd_issue<2, P2>(a, &map2, r, in_buf, &full[slot], &ring[slot]);
         item += gridDim.x;
         resolve(item, &rn);  // look one tile ahead
+        // ... and pull the input of the phase-0 tile `a.prefetch_ahead` items further on from HBM into L2 now: the copy
+        // that stages it then finds it in L2, so fewer bytes have to be in flight per SM to cover the HBM latency
+        if (a.prefetch_ahead > 0) {
+          const unsigned pit = item + (unsigned)(a.prefetch_ahead - 1) * gridDim.x;
+          if (pit < a.total_items) {
+            NdLocate pl{loc.seg};
+            int pphase;
+            long long pg;
+            pl.find(a, pit, &pphase, &pg);
+            if (pphase == 0) {
+              const long long pt = pg / a.ph[0].tiles_per_transform;
+              P0::prefetch(a.ph[0], reinterpret_cast<const char*>(a.in) + pt * a.in_stride_bytes,
+                           (int)(pg - pt * a.ph[0].tiles_per_transform));
+            }
+          }
+        }
       }
     }
     return;
@@ -461,8 +509,8 @@ __global__ void __launch_bounds__(NT + 32, MINB)
 
   // ---------------- consumers
   for (unsigned k = 0;; ++k) {
-    const int slot = k % ND_RING;
-    tma::mbar_wait(&full[slot], (k / ND_RING) & 1);
+    const int slot = k % RING;
+    tma::mbar_wait(&full[slot], (k / RING) & 1);
     const NdItem it = ring[slot];
     if (it.phase < 0) break;
     const void* in_buf = base + slot * IN;

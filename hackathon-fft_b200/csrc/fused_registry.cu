@@ -105,6 +105,7 @@ struct FusedPass : Pass {
     return B200FFT_OK;
   }
 
+  int prefetch_ahead = 0;     // (measured: no gain at 1-2, loses from 4 on; profiles/r2_prefetch_sweep.log) B200FFT_PREFETCH_AHEAD: L2 prefetch distance of the v2 producer, in items of its own CTA
   unsigned* h_err = nullptr;  // mapped host word the kernels raise when a dependency wait gives up
   unsigned* d_err = nullptr;
   bool use_fallback = false;  // a cooperative launch was refused once: stay on the per-axis kernels
@@ -140,6 +141,7 @@ struct FusedPass : Pass {
     a.total_items = pb->total_items;
     a.ctrl = pb->d_ctrl;
     a.err = d_err;
+    a.prefetch_ahead = prefetch_ahead;
     for (int p = 0; p < ND_MAX_PHASES; ++p) a.cnt_off[p] = pb->cnt_off[p];
     a.nwords = pb->nwords;
     const unsigned grid = (unsigned)std::min<long long>(pb->total_items, max_grid);
@@ -286,7 +288,9 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
   const bool inv = p.desc.inverse != 0;
   double total_scale = 1.0;
   for (int a = 0; a < p.rank; ++a) total_scale *= (double)dims[a];
-  long long chunk_mb = 8;  // 64^3 x100: 8 -> 0.1472, 12 -> 0.1464, 16 -> 0.1483 ms; 128^3 x10: 8 -> 0.1457, 12 -> 0.1474
+  // 64^3 x100: 8 -> 0.1472, 12 -> 0.1464, 16 -> 0.1483 ms; 128^3 x10: 8 -> 0.1457, 12 -> 0.1474;
+  // half spectrum 64^3 x100 (tiles half the size): 8 -> 0.1012, 16 -> 0.0982, 24 -> 0.0944 (t160)
+  long long chunk_mb = p.half ? 16 : 8;
   if (const char* e = getenv("B200FFT_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));
   std::string desc;
   for (int q = 0; q < v.nphases; ++q) {
@@ -295,7 +299,14 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
     SchedPhase& S = pass->sched[q];
     const int a = pick_axes[q];
     const bool lastp = q == v.nphases - 1;
-    if (!upload(build_twiddles(ph.radices, inv), &P.tw)) return nullptr;
+    {
+      std::vector<float2> table = build_twiddles(ph.radices, inv);
+      if (ph.kind == ND_R2C_PLANE) {  // [x stage twiddles | W_n^k, k = 0..n/2]: one table, staged once per CTA
+        const std::vector<float2> half = build_half_twiddles(dims[last], false);
+        table.insert(table.end(), half.begin(), half.end());
+      }
+      if (!upload(table, &P.tw)) return nullptr;
+    }
     P.scale = 1.f;
     P.do_scale = 0;
     long long tile_bytes = 0;
@@ -310,7 +321,6 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
       P.tiles_per_transform = (int)P.units_per_transform;
       P.tiles_per_outer = 1;
       if (!upload(build_twiddles(ph.radices2, inv), &P.tw2)) return nullptr;
-      if (ph.kind == ND_R2C_PLANE && !upload(build_half_twiddles(dims[last], false), &P.tw3)) return nullptr;
       tile_bytes = cdims[last] * dims[last - 1] * 8;
     } else {  // ND_COLS on axis a
       P.inner = prod(cdims, a + 1, cdims.size());
@@ -365,6 +375,7 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
     return nullptr;
   }
   pass->max_grid = occ * plan.sm_count;
+  if (const char* e = getenv("B200FFT_PREFETCH_AHEAD")) pass->prefetch_ahead = std::max(0, atoi(e));
   if (v.async) {
     int coop = 0;
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, plan.device) != cudaSuccess || !coop) {

@@ -49,7 +49,7 @@ struct FusedV {
 // must be resident at the same time. A cooperative launch is the CUDA guarantee for exactly that (the launch waits until
 // the whole grid fits, and is refused with cudaErrorCooperativeLaunchTooLarge when it never can: MPS / green-context
 // partitions with fewer SMs than the plan saw).
-template <int NT, int MINB, class P0, class P1, class P2>
+template <int NT, int MINB, class P0, class P1, class P2, int RING = ND_RING>
 struct FusedAsyncV {
   static cudaError_t launch(const NdArgs& a, const CUtensorMap& m1, const CUtensorMap& m2, unsigned grid, size_t smem,
                             cudaStream_t st) {
@@ -63,7 +63,7 @@ struct FusedAsyncV {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, nd_async_kernel<NT, MINB, P0, P1, P2>, a, m1, m2);
+    return cudaLaunchKernelEx(&cfg, nd_async_kernel<NT, MINB, P0, P1, P2, RING>, a, m1, m2);
   }
 };
 
@@ -119,7 +119,7 @@ void reg_fused(std::vector<int> dims, int mode, const char* tag = "") {
 }
 
 // v2 variants: <consumer threads, min CTAs per SM, async phase types...>(dims, mode)
-template <int NT, int MINB, class P0, class P1, class P2 = ANone>
+template <int NT, int MINB, class P0, class P1, class P2 = ANone, int RING = ND_RING>
 void reg_fused_async(std::vector<int> dims, int mode, const char* tag = "", int default_min_batch = 0) {
   FusedVariant v;
   v.dims = dims;
@@ -130,11 +130,11 @@ void reg_fused_async(std::vector<int> dims, int mode, const char* tag = "", int 
   v.ph[1] = fused_phase_info<P1>();
   v.ph[2] = fused_phase_info<P2>();
   v.threads = NT + 32;
-  v.smem = nd_async_smem<P0, P1, P2>();
+  v.smem = nd_async_smem<P0, P1, P2, RING>();
   v.async = true;
   v.default_min_batch = default_min_batch;
-  v.launch_async = &FusedAsyncV<NT, MINB, P0, P1, P2>::launch;
-  v.func = (const void*)nd_async_kernel<NT, MINB, P0, P1, P2>;
+  v.launch_async = &FusedAsyncV<NT, MINB, P0, P1, P2, RING>::launch;
+  v.func = (const void*)nd_async_kernel<NT, MINB, P0, P1, P2, RING>;
   std::string name = "ndA";
   for (size_t i = 0; i < dims.size(); ++i) name += (i ? "x" : "") + std::to_string(dims[i]);
   name += std::string(v.inverse ? "_inv" : "") + (mode == 1 ? "_real" : mode == 2 ? "_r2c" : "") + "_t" + std::to_string(NT) +

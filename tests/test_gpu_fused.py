@@ -66,9 +66,15 @@ CASES = [
     ((5, 640, 480), False, "real", "ndA640"),
     ((1, 640, 480), False, "c2c", "ndA640"),
     # half-spectrum 3-D: (y, x) planes with unpack + y pass in shared memory (AR2CPlane), then the strided z phase
-    ((5, 64, 64, 64), False, "half", "r2cplane64x64(8x8;2;8x4)_z32"),
-    ((37, 64, 64, 64), False, "half", "r2cplane64x64(8x8;2;8x4)_z32"),
+    ((5, 64, 64, 64), False, "half", "t288+32_r2cplane64x64(8x8;2;8x4)_z32:"),
+    ((37, 64, 64, 64), False, "half", "t288+32_r2cplane64x64(8x8;2;8x4)_z32:"),
     ((3, 64, 64, 64), False, "half", "r2cplane64x64(8x8;2;8x4)_z64"),
+    ((7, 64, 64, 64), False, "half", "z32_t160_zslot"),
+    ((41, 64, 64, 64), False, "half", "z32_t128_zslot"),
+    ((5, 128, 128, 128), False, "half", "r2cplane128x128(16x8;2;8x8)_z32_t384"),
+    ((9, 64, 64, 64), False, "c2c", "z32_t128_r1"),
+    ((9, 64, 64, 64), True, "c2c", "z64_t256_r1"),
+    ((30, 64, 64, 64), False, "c2c", "z32_t192_r1"),
 ]
 
 
