@@ -17,10 +17,7 @@
 // Everything is __host__ __device__ so tests/test_codelets.py can check every
 // instantiation against a naive DFT on the CPU (csrc/codelet_selftest.cu).
 #pragma once
-#include <cuda_runtime.h>
-
-#include <type_traits>
-#include <utility>
+#include "rtc_prelude.cuh"
 
 namespace b200fft {
 

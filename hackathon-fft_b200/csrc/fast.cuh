@@ -15,7 +15,7 @@
 //   cols   : O = 1, CN = columns per tile  (strided axis; no transpose kernel)
 //   planes : both, back to back, for 2-D tiles that fit shared memory
 #pragma once
-#include <cuda_runtime.h>
+#include "rtc_prelude.cuh"
 
 #include "dft.cuh"
 #include "tma.cuh"

@@ -8,7 +8,7 @@
 //                          (see make_fused_pass; plan flag B200FFT_FLAG_NO_FUSED always wins)
 //   B200FFT_CHUNK_MB=<n>   pipeline chunk size (default 8): how much phase-0 output is produced per
 //                          round; ~2-3 chunks are live in L2 at any time
-//   B200FFT_FUSED_PREFER=substr   prefer variants whose name contains substr (tuning aid)
+//   B200FFT_FUSED_PREFER=substr   prefer variants whose name contains substr (tuning aid; "substr:" = name ENDS with it)
 // The v2 kernels (static work assignment) are launched COOPERATIVELY: the driver guarantees the whole grid is
 // co-resident or refuses the launch, in which case the pass runs the plan's per-axis kernels instead (Pass::fallback).
 #include <cuda_runtime.h>
@@ -212,7 +212,13 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan) {
   std::vector<int> pick_axes;
   for (int round = prefer ? 0 : 1; round < 2 && !pick; ++round) {  // round 0: preferred names only
     for (const FusedVariant& v : fused_registry()) {
-      if (round == 0 && v.name.find(prefer) == std::string::npos) continue;
+      if (round == 0) {  // substring of the variant name; a trailing ':' anchors it at the END of the name
+        std::string want(prefer);
+        const bool anchored = !want.empty() && want.back() == ':';
+        if (anchored) want.pop_back();
+        const size_t at = anchored ? v.name.rfind(want) : v.name.find(want);
+        if (at == std::string::npos || (anchored && at + want.size() != v.name.size())) continue;
+      }
       if (mode_env < 0 && (v.default_min_batch <= 0 || p.batch < v.default_min_batch)) continue;
       if ((int)v.dims.size() != p.rank || v.inverse != (p.desc.inverse != 0) || v.mode != mode) continue;
       bool ok = true;

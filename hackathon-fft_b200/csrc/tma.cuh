@@ -1,9 +1,7 @@
 // Thin inline-PTX wrappers for the sm_100a bulk-tensor (TMA) path used by the strided-axis pass:
 // mbarrier init / expect_tx / parity wait, cp.async.bulk.tensor.3d loads and stores.
 #pragma once
-#include <cuda.h>
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "rtc_prelude.cuh"
 
 namespace b200fft {
 namespace tma {

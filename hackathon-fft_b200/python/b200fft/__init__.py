@@ -18,12 +18,14 @@ import os
 
 __all__ = ["plan_fft", "fft", "Plan", "SlabPlan", "B200FFTError", "ordered_bases", "default_bases", "dry_run",
            "launch_count", "lib_path", "REAL_FULL", "REAL_HALF", "FLAG_FORCE_GENERIC", "FLAG_NO_FUSED", "FLAG_PREFER_FUSED",
-           "FLAG_FORCE_RT", "GPUTest", "stream_synchronize", "host_register", "host_unregister"]
+           "FLAG_FORCE_RT", "GPUTest", "stream_synchronize", "host_register", "host_unregister", "MgpuPlan", "mgpu_split",
+           "MGPU_BATCH_SHARD", "MGPU_SLAB"]
 
 MAX_RANK = 8
 U8, F32, F64 = 0, 1, 2
 REAL_FULL, REAL_HALF = 0, 1
 FLAG_FORCE_GENERIC, FLAG_NO_FUSED, FLAG_PREFER_FUSED, FLAG_FORCE_RT = 1, 4, 8, 16
+MGPU_BATCH_SHARD, MGPU_SLAB = 0, 1
 
 
 class GPUTest:
@@ -89,6 +91,20 @@ SYMBOLS = [
     ("b200fft_slab_describe", ctypes.c_size_t, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
     ("b200fft_slab_destroy", ctypes.c_int, [_vp]),
     ("b200fft_plan_destroy", ctypes.c_int, [_vp]),
+    ("b200fft_mgpu_plan_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_Desc), ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    ("b200fft_mgpu_plan_destroy", ctypes.c_int, [_vp]),
+    ("b200fft_mgpu_ngpu", ctypes.c_int, [_vp]),
+    ("b200fft_mgpu_shard", ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    ("b200fft_mgpu_in_bytes", ctypes.c_size_t, [_vp, ctypes.c_int]),
+    ("b200fft_mgpu_out_bytes", ctypes.c_size_t, [_vp, ctypes.c_int]),
+    ("b200fft_mgpu_exec", ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    ("b200fft_mgpu_synchronize", ctypes.c_int, [_vp]),
+    ("b200fft_mgpu_stream", _vp, [_vp, ctypes.c_int]),
+    ("b200fft_mgpu_exec_host", ctypes.c_int, [_vp, _vp, _vp]),
+    ("b200fft_mgpu_describe", ctypes.c_size_t, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
+    ("b200fft_mgpu_split", ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                           ctypes.POINTER(ctypes.c_int64)]),
     ("b200fft_plan_workspace_bytes", ctypes.c_size_t, [_vp]),
     ("b200fft_plan_get_bases", ctypes.c_int, [_vp, ctypes.c_int, _u32p, ctypes.c_int]),
     ("b200fft_plan_describe", ctypes.c_size_t, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
@@ -380,6 +396,77 @@ class SlabPlan:
     def destroy(self):
         if self._h:
             lib().b200fft_slab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def mgpu_split(batch, ngpu, g):
+    """(first, count) of the batch items device slot g owns under MGPU_BATCH_SHARD (host-only rule)."""
+    first, count = ctypes.c_int64(), ctypes.c_int64()
+    if lib().b200fft_mgpu_split(batch, ngpu, g, ctypes.byref(first), ctypes.byref(count)) != 0:
+        raise B200FFTError(1, "mgpu_split(%r, %r, %r)" % (batch, ngpu, g))
+    return int(first.value), int(count.value)
+
+
+class MgpuPlan:
+    """One host process driving several GPUs (b200fft_mgpu_*): batch sharding without communication, or the slab
+    decomposition of ONE 3-D transform with the exchange fused into the Y pass's peer-to-peer stores."""
+
+    def __init__(self, in_dtype, out_dtype, in_layout, out_layout, *, devices, mode=MGPU_BATCH_SHARD, bases=None,
+                 inverse=False, real_mode=REAL_FULL, flags=0):
+        d, keep = _make_desc(in_dtype, out_dtype, in_layout, out_layout, bases, inverse, real_mode, 0, None, flags)
+        devs = [int(v) for v in devices]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        h = ctypes.c_void_p()
+        _check(lib().b200fft_mgpu_plan_create(ctypes.byref(h), ctypes.byref(d), len(devs), arr, mode))
+        self._h = h
+        self.devices, self.mode = devs, mode
+
+    @property
+    def ngpu(self):
+        return int(lib().b200fft_mgpu_ngpu(self._h))
+
+    def shard(self, g):
+        first, count = ctypes.c_int64(), ctypes.c_int64()
+        _check(lib().b200fft_mgpu_shard(self._h, g, ctypes.byref(first), ctypes.byref(count)))
+        return int(first.value), int(count.value)
+
+    def in_bytes(self, g):
+        return int(lib().b200fft_mgpu_in_bytes(self._h, g))
+
+    def out_bytes(self, g):
+        return int(lib().b200fft_mgpu_out_bytes(self._h, g))
+
+    def stream(self, g):
+        return lib().b200fft_mgpu_stream(self._h, g)
+
+    def exec(self, outs, ins):
+        """Enqueue on every slot's stream; outs[g] / ins[g] live on device slot g. Call synchronize() before reading."""
+        o = (ctypes.c_void_p * len(outs))(*[_ptr(t) for t in outs])
+        i = (ctypes.c_void_p * len(ins))(*[_ptr(t) for t in ins])
+        _check(lib().b200fft_mgpu_exec(self._h, o, i))
+
+    def synchronize(self):
+        _check(lib().b200fft_mgpu_synchronize(self._h))
+
+    def exec_host(self, h_out, h_in):
+        """The whole job from / to host memory in natural order, spread over the devices; blocks until h_out is complete."""
+        _check(lib().b200fft_mgpu_exec_host(self._h, _ptr(h_out), _ptr(h_in)))
+
+    def describe(self):
+        n = lib().b200fft_mgpu_describe(self._h, None, 0)
+        buf = ctypes.create_string_buffer(int(n) + 1)
+        lib().b200fft_mgpu_describe(self._h, buf, len(buf))
+        return buf.value.decode()
+
+    def destroy(self):
+        if self._h:
+            lib().b200fft_mgpu_plan_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -177,6 +177,45 @@ B200FFT_API int b200fft_slab_destroy(b200fft_slab* slab);
 
 B200FFT_API int b200fft_plan_destroy(b200fft_plan* plan);
 
+/* ---- Multi-device entry points: ONE host process drives several GPUs of a node. The reference has
+ * no multi-GPU path; a Mojo host owns one DeviceContext per GPU and would otherwise have to re-implement the sharding
+ * and the slab orchestration that python/b200fft/slab.py does over torch.distributed. Device slot g runs on CUDA
+ * ordinal devices[g] (devices == NULL: ordinals 0..ngpu-1) on a plan-owned non-blocking stream.
+ *
+ *   B200FFT_MGPU_BATCH_SHARD  `desc` describes the WHOLE job; slot g owns the contiguous batch items
+ *                             [first_g, first_g + count_g) (the first batch % ngpu slots hold one more). No
+ *                             communication. d_in[g] / d_out[g] hold only that slot's items.
+ *   B200FFT_MGPU_SLAB         one 3-D complex fp32 transform (batch 1, dims (Z, Y, X), Z and Y divisible by ngpu). Slot g
+ *                             holds the input z planes [g Z/G, (g+1) Z/G) as d_in[g][Z/G][Y][X]; after exec d_out[h] holds
+ *                             out[z][y_local][x] for y = h Y/G + y_local, i.e. d_out[h][Z][Y/G][X] ("transposed out", as
+ *                             the slab decomposition of north_star leaves it). Local (Y, X) transform with the exchange
+ *                             fused into the Y pass's stores (peer-to-peer over NVLink, cudaDeviceEnablePeerAccess, no
+ *                             pack buffer, no all-to-all), device-side event barrier, strided Z pass in place on d_out.
+ *                             d_out[] must be peer-accessible device memory (cudaMalloc / b200fft_malloc).
+ *
+ * exec enqueues on every slot's stream and returns; b200fft_mgpu_synchronize waits for all of them.
+ * b200fft_mgpu_stream(plan, g) is that stream (a cudaStream_t) for callers that order their own work against it.
+ * exec_host takes the WHOLE job in host memory, natural order (SLAB: h_in[Z][Y][X] -> h_out[Z][Y][X]): every slot
+ * copies its share in, runs, and copies its share out (one host thread per slot for BATCH_SHARD, each running the
+ * chunked 3-stream pipeline of b200fft_exec_host); returns when h_out is complete. */
+enum { B200FFT_MGPU_BATCH_SHARD = 0, B200FFT_MGPU_SLAB = 1 };
+typedef struct b200fft_mgpu_plan b200fft_mgpu_plan;
+B200FFT_API int b200fft_mgpu_plan_create(b200fft_mgpu_plan** plan, const b200fft_desc* desc, int ngpu, const int* devices,
+                                         int mode);
+B200FFT_API int b200fft_mgpu_plan_destroy(b200fft_mgpu_plan* plan);
+B200FFT_API int b200fft_mgpu_ngpu(const b200fft_mgpu_plan* plan);
+/* what slot g holds on input: batch items (BATCH_SHARD) or z planes (SLAB) [*first, *first + *count) */
+B200FFT_API int b200fft_mgpu_shard(const b200fft_mgpu_plan* plan, int g, int64_t* first, int64_t* count);
+B200FFT_API size_t b200fft_mgpu_in_bytes(const b200fft_mgpu_plan* plan, int g);
+B200FFT_API size_t b200fft_mgpu_out_bytes(const b200fft_mgpu_plan* plan, int g);
+B200FFT_API int b200fft_mgpu_exec(b200fft_mgpu_plan* plan, void* const* d_out, const void* const* d_in);
+B200FFT_API int b200fft_mgpu_synchronize(b200fft_mgpu_plan* plan);
+B200FFT_API void* b200fft_mgpu_stream(const b200fft_mgpu_plan* plan, int g);
+B200FFT_API int b200fft_mgpu_exec_host(b200fft_mgpu_plan* plan, void* h_out, const void* h_in);
+B200FFT_API size_t b200fft_mgpu_describe(const b200fft_mgpu_plan* plan, char* buf, size_t cap);
+/* host-only: the batch split BATCH_SHARD uses (no CUDA call) */
+B200FFT_API int b200fft_mgpu_split(int64_t batch, int ngpu, int g, int64_t* first, int64_t* count);
+
 /* ---- introspection (tests, harness) */
 B200FFT_API size_t b200fft_plan_workspace_bytes(const b200fft_plan* plan);
 /* ordered stage list of an axis, the reference's `_get_ordered_bases_processed_list`

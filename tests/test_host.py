@@ -238,3 +238,28 @@ print(*seen[0], L.b200fft_variant_count(7))
         assert fast >= 40 and fused >= 10 and split >= 8 and unknown == -1, r.stdout
     # and the in-process view agrees (tables are per process, sizes are a property of the build)
     assert b200fft.lib().b200fft_variant_count(0) == fast
+
+
+def test_mgpu_batch_split_rule():
+    """BATCH_SHARD's split (b200fft_mgpu_split, host-only): contiguous, covers the batch, sizes differ by at most one,
+    the larger shares first (10 items over 4 devices -> 3/3/2/2, 100 over 8 -> 13 x 4 + 12 x 4)."""
+    for batch, n in ((10, 4), (100, 8), (500000, 8), (7, 7), (1, 1), (9, 2)):
+        nxt, sizes = 0, []
+        for g in range(n):
+            first, count = b200fft.mgpu_split(batch, n, g)
+            assert first == nxt
+            nxt += count
+            sizes.append(count)
+        assert nxt == batch and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert [b200fft.mgpu_split(10, 4, g)[1] for g in range(4)] == [3, 3, 2, 2]
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.mgpu_split(10, 4, 4)
+
+
+def test_mgpu_needs_cuda_no_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(b200fft.B200FFTError) as e:
+        b200fft.MgpuPlan("float32", "float32", (8, 64, 2), (8, 64, 2), devices=[0])
+    assert e.value.status == 5
