@@ -72,6 +72,7 @@ std::unique_ptr<Pass> make_pass(b200fft_plan* plan, int axis, const AxisView& vi
     if (!(p.desc.flags & B200FFT_FLAG_FORCE_RT)) {
       pass = make_fast_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
       if (!pass) pass = make_split_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
+      if (!pass) pass = make_jit_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
     }
     if (!pass) pass = make_rt_pass(*plan, axis, view, src, p.desc.inverse != 0, half);
   }
@@ -282,6 +283,27 @@ int b200fft_ordered_bases(uint64_t length, const uint32_t* bases, int nbases, ui
 
 int b200fft_default_bases(uint64_t length, int gpu_target, uint32_t* out, int cap) {
   return copy_bases(estimate_best_bases(length, gpu_target != 0), out, cap);
+}
+
+int b200fft_jit_probe(int64_t n, int64_t inner, const uint32_t* bases, int nbases, int inverse, int real_in, int half,
+                      char* buf, size_t cap) {
+  if (half < 0 || half > 2) return fail(B200FFT_ERR_INVALID_ARG, "half = %d (0 complex, 1 R2C, 2 C2R)", half);
+  if (n < 2 || inner < 1) return fail(B200FFT_ERR_INVALID_ARG, "axis length %lld, inner %lld", (long long)n, (long long)inner);
+  std::vector<uint32_t> ordered;
+  if (bases && nbases > 0) {
+    ordered = build_ordered_bases((uint64_t)n, std::vector<uint32_t>(bases, bases + nbases));
+  } else {
+    ordered = build_ordered_bases((uint64_t)n, estimate_best_bases((uint64_t)n, true));
+  }
+  if (!ordered_bases_valid((uint64_t)n, ordered)) return fail(B200FFT_ERR_BASES, "bases do not factor %lld", (long long)n);
+  std::string report;
+  const int rc = jit_probe(n, inner, ordered, inverse != 0, real_in != 0, half, &report);
+  if (rc != B200FFT_OK) return rc;
+  if (buf && cap) {
+    strncpy(buf, report.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+  }
+  return B200FFT_OK;
 }
 
 int b200fft_schedule_dry_run(int nphases, const int64_t* phases, int64_t batch, int64_t* segments, int cap) {

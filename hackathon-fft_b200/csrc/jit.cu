@@ -1,0 +1,642 @@
+// Plan-time specialisation tier: the compile-time kernels of fast.cuh instantiated at plan creation for axis lengths
+// that have no hand-registered variant.
+//
+// The reference specialises EVERY shape at compile time (Mojo `comptime` parameters: length, bases, layouts are all
+// template arguments of `_intra_something_gpu_fft_kernel_radix_n_multi_dim`, _ndim_fft_gpu.mojo:279-450). A C ABI
+// takes them at run time, so the equivalent here is run-time compilation: `b200fft_plan_create` hands the very same
+// headers the registered variants are built from (rtc_prelude.cuh, dft.cuh, tma.cuh, fast.cuh — embedded in the
+// library as text) to NVRTC with the axis length, the grouped super-stage list, the tile shape and the direction as
+// template arguments, gets a cubin for sm_100a back, loads it with the driver API and launches it like any other pass.
+// One compile per distinct (kind, N, radices, tile, threads, direction, input kind) per device, cached for the life of
+// the process. If libnvrtc cannot be loaded or the compile fails, the axis falls to the runtime-length tier (rt.cu).
+//   B200FFT_JIT=0        disable this tier          B200FFT_JIT_VERBOSE=1   print compile times / logs to stderr
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fast_registry.hpp"
+#include "plan.hpp"
+
+namespace b200fft {
+
+namespace {
+
+#include "jit_embed.inc"  // k_src_rtc_prelude, k_src_dft, k_src_tma, k_src_fast: the device headers as text
+
+// ---- NVRTC, loaded lazily (no link-time dependency) ----------------------------------------------------------------
+struct Nvrtc {
+  using Program = void*;
+  int (*CreateProgram)(Program*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*DestroyProgram)(Program*) = nullptr;
+  int (*CompileProgram)(Program, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(Program, size_t*) = nullptr;
+  int (*GetCUBIN)(Program, char*) = nullptr;
+  int (*GetProgramLogSize)(Program, size_t*) = nullptr;
+  int (*GetProgramLog)(Program, char*) = nullptr;
+  int (*AddNameExpression)(Program, const char*) = nullptr;
+  int (*GetLoweredName)(Program, const char*, const char**) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+const Nvrtc& nvrtc() {
+  static const Nvrtc api = [] {
+    Nvrtc n;
+    void* h = nullptr;
+    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (h) break;
+    }
+    if (!h) {
+      n.why = "libnvrtc.so.12 not found";
+      return n;
+    }
+    auto sym = [&](const char* s) { return dlsym(h, s); };
+#define B200_NVRTC_SYM(field, name) \
+  n.field = reinterpret_cast<decltype(n.field)>(sym(name)); \
+  if (!n.field) { n.why = std::string("missing ") + name; return n; }
+    B200_NVRTC_SYM(CreateProgram, "nvrtcCreateProgram")
+    B200_NVRTC_SYM(DestroyProgram, "nvrtcDestroyProgram")
+    B200_NVRTC_SYM(CompileProgram, "nvrtcCompileProgram")
+    B200_NVRTC_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    B200_NVRTC_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    B200_NVRTC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    B200_NVRTC_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    B200_NVRTC_SYM(AddNameExpression, "nvrtcAddNameExpression")
+    B200_NVRTC_SYM(GetLoweredName, "nvrtcGetLoweredName")
+    B200_NVRTC_SYM(GetErrorString, "nvrtcGetErrorString")
+#undef B200_NVRTC_SYM
+    n.ok = true;
+    return n;
+  }();
+  return api;
+}
+
+// ---- driver entry points through the runtime (no link against libcuda, like the tensor-map encoder) ----------------
+struct Driver {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**,
+                           void**) = nullptr;
+  bool ok = false;
+};
+
+const Driver& driver() {
+  static const Driver api = [] {
+    Driver d;
+    auto get = [](const char* name) -> void* {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      return p;
+    };
+    d.ModuleLoadData = reinterpret_cast<decltype(d.ModuleLoadData)>(get("cuModuleLoadData"));
+    d.ModuleUnload = reinterpret_cast<decltype(d.ModuleUnload)>(get("cuModuleUnload"));
+    d.ModuleGetFunction = reinterpret_cast<decltype(d.ModuleGetFunction)>(get("cuModuleGetFunction"));
+    d.ModuleGetGlobal = reinterpret_cast<decltype(d.ModuleGetGlobal)>(get("cuModuleGetGlobal"));
+    d.FuncSetAttribute = reinterpret_cast<decltype(d.FuncSetAttribute)>(get("cuFuncSetAttribute"));
+    d.FuncGetAttribute = reinterpret_cast<decltype(d.FuncGetAttribute)>(get("cuFuncGetAttribute"));
+    d.LaunchKernel = reinterpret_cast<decltype(d.LaunchKernel)>(get("cuLaunchKernel"));
+    d.ok = d.ModuleLoadData && d.ModuleUnload && d.ModuleGetFunction && d.ModuleGetGlobal && d.FuncSetAttribute && d.FuncGetAttribute && d.LaunchKernel;
+    return d;
+  }();
+  return api;
+}
+
+// ---- what to compile ------------------------------------------------------------------------------------------------
+enum JitKind {
+  JIT_ROWS = 0,     // rows_kernel<N, RL, C, NT, INV, REAL>: `tile` contiguous transforms per CTA
+  JIT_COLS,         // cols_kernel<N, RL, CW, NT, INV, REAL>: all N points of `tile` adjacent columns of a strided axis
+  JIT_SCATTER,      // cols_scatter_kernel<N, RL, CW, NT, INV>: the same with the slab exchange in its stores
+  JIT_R2C,          // rows_r2c_kernel<H, RL, C, NT>: n = 2H real points as an H-point complex row + shared-memory unpack
+  JIT_R2C_REG,      // rows_r2c_reg_kernel<H, RL, C, NT>: Hermitian unpack in registers (warp shuffles)
+  JIT_R2C_ODD,      // rows_r2c_odd_kernel<N, RL, C, NT>: odd n, the n-point row kernel on real rows, bins 0..n/2 stored
+  JIT_C2R           // rows_c2r_kernel<H, RL, C, NT>: Hermitian pack fused into stage 0 of the H-point inverse
+};
+
+struct JitSpec {
+  JitKind kind = JIT_ROWS;
+  int n = 0;  // length of the complex transform the kernel runs (H = n_real / 2 for R2C / R2C_REG / C2R)
+  std::vector<int> radices;
+  int tile = 0, threads = 0;
+  bool inverse = false, real_in = false, packed = false;
+
+  bool strided() const { return kind == JIT_COLS || kind == JIT_SCATTER; }
+  std::string radix_list() const {
+    std::string s;
+    for (int r : radices) s += (s.empty() ? "" : ", ") + std::to_string(r);
+    return s;
+  }
+  std::string shape_args() const {  // "<N, Radices<...>, tile" shared by every kernel and smem-size template
+    return std::to_string(n) + ", b200fft::Radices<" + radix_list() + ">, " + std::to_string(tile);
+  }
+  std::string expression() const {  // the template-id NVRTC instantiates
+    const std::string head = shape_args() + ", " + std::to_string(threads);
+    const char* inv = inverse ? "true" : "false";
+    const char* real = real_in ? "true" : "false";
+    switch (kind) {
+      case JIT_ROWS: return "b200fft::rows_kernel<" + head + ", " + inv + ", " + real + ">";
+      case JIT_COLS: return "b200fft::cols_kernel<" + head + ", " + inv + ", " + real + ">";
+      case JIT_SCATTER: return "b200fft::cols_scatter_kernel<" + head + ", " + inv + ">";
+      case JIT_R2C: return "b200fft::rows_r2c_kernel<" + head + ">";
+      case JIT_R2C_REG: return "b200fft::rows_r2c_reg_kernel<" + head + ">";
+      case JIT_R2C_ODD: return "b200fft::rows_r2c_odd_kernel<" + head + ">";
+      default: return "b200fft::rows_c2r_kernel<" + head + ">";
+    }
+  }
+  std::string smem_expression() const {  // fast.cuh's own constexpr for the instantiation's dynamic shared memory
+    switch (kind) {
+      case JIT_ROWS:
+      case JIT_R2C_ODD: return "b200fft::rows_smem_bytes<" + shape_args() + ">()";
+      case JIT_COLS:
+      case JIT_SCATTER: return "b200fft::cols_smem_bytes<" + shape_args() + ">()";
+      case JIT_R2C: return "b200fft::rows_r2c_smem_bytes<" + shape_args() + ">()";
+      case JIT_R2C_REG: return "b200fft::rows_r2c_reg_smem_bytes<" + shape_args() + ">()";
+      default: return "b200fft::rows_c2r_smem_bytes<" + shape_args() + ">()";
+    }
+  }
+  std::string name() const {
+    static const char* const tag[] = {"jitrows", "jitcols", "jitscatter", "jitr2c", "jitr2creg", "jitr2codd", "jitc2r"};
+    return std::string(tag[kind]) + std::to_string(n) + "_" + radix_name(radices) + (strided() ? "_w" : "_c") + std::to_string(tile) +
+           "_t" + std::to_string(threads);
+  }
+  std::string key() const { return expression() + (packed ? "|p" : "|s"); }
+  // Host mirror of the smem_expression() formulas (fast.cuh): used to choose the tile before anything is compiled, and
+  // checked against the value the compiled module reports (b200fft_jit_smem_bytes) when it is loaded.
+  // RowLayout pads a Q-block by P elements when P < 16, Q even and Q < N; DenseLayout is N x CW.
+  size_t smem() const {
+    long long P = 1, ex = 0;
+    for (size_t s = 0; s + 1 < radices.size(); ++s) {
+      const long long Q = P * radices[s];
+      long long elems;
+      if (strided()) {
+        elems = (long long)n * tile;
+      } else {
+        const bool padded = P < 16 && Q % 2 == 0 && Q < n;
+        elems = (long long)tile * (padded ? n + n / Q * P : n);
+      }
+      ex = std::max(ex, elems);
+      P = Q;
+    }
+    const size_t pingpong = radices.size() > 2 ? 2 : 1;
+    switch (kind) {
+      case JIT_R2C: return sizeof(float2) * (size_t)std::max<long long>(ex, (long long)tile * n) * 2;
+      case JIT_C2R: return sizeof(float2) * ((size_t)ex * 2 + (size_t)tile * (n + 1));
+      default: return sizeof(float2) * (size_t)ex * pingpong;
+    }
+  }
+};
+
+struct JitKernel {
+  CUmodule module = nullptr;
+  CUfunction fn = nullptr;
+  int regs = 0, local_bytes = 0;
+  size_t cubin_bytes = 0;
+  double compile_ms = 0;
+};
+
+// compile `spec` to a cubin for sm_100a; `lowered` receives the kernel's mangled name
+int compile(const JitSpec& spec, std::vector<char>* cubin, std::string* lowered, std::string* log, double* ms) {
+  const Nvrtc& rtc = nvrtc();
+  if (!rtc.ok) return fail(B200FFT_ERR_UNSUPPORTED, "run-time compilation unavailable: %s", rtc.why.c_str());
+  const auto t0 = std::chrono::steady_clock::now();
+  std::string src;
+  if (spec.packed) src += "#define B200FFT_PACKED 1\n";
+  src += "#include \"fast.cuh\"\n";
+  src += "extern \"C\" __device__ unsigned long long b200fft_jit_smem_bytes = (unsigned long long)" + spec.smem_expression() + ";\n";
+  const char* headers[] = {k_src_rtc_prelude, k_src_dft, k_src_tma, k_src_fast};
+  const char* names[] = {"rtc_prelude.cuh", "dft.cuh", "tma.cuh", "fast.cuh"};
+  Nvrtc::Program prog = nullptr;
+  int rc = rtc.CreateProgram(&prog, src.c_str(), "b200fft_jit.cu", 4, headers, names);
+  if (rc) return fail(B200FFT_ERR_CUDA, "nvrtcCreateProgram: %s", rtc.GetErrorString(rc));
+  const std::string expr = spec.expression();
+  rc = rtc.AddNameExpression(prog, expr.c_str());
+  // -default-device: the headers' plain constexpr helpers (index arithmetic, compile-time trigonometry) are device
+  // functions here, which is what --expt-relaxed-constexpr gives them under nvcc
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+  if (!rc) rc = rtc.CompileProgram(prog, 4, opts);
+  size_t ln = 0;
+  if (rtc.GetProgramLogSize(prog, &ln) == 0 && ln > 1) {
+    log->resize(ln);
+    rtc.GetProgramLog(prog, &(*log)[0]);
+  }
+  if (rc) {
+    rtc.DestroyProgram(&prog);
+    return fail(B200FFT_ERR_CUDA, "NVRTC could not compile %s: %s\n%s", expr.c_str(), rtc.GetErrorString(rc), log->c_str());
+  }
+  const char* low = nullptr;
+  size_t nb = 0;
+  if ((rc = rtc.GetLoweredName(prog, expr.c_str(), &low)) || (rc = rtc.GetCUBINSize(prog, &nb)) || nb == 0) {
+    rtc.DestroyProgram(&prog);
+    return fail(B200FFT_ERR_CUDA, "NVRTC produced no cubin for %s", expr.c_str());
+  }
+  *lowered = low;
+  cubin->resize(nb);
+  rc = rtc.GetCUBIN(prog, cubin->data());
+  rtc.DestroyProgram(&prog);
+  if (rc) return fail(B200FFT_ERR_CUDA, "nvrtcGetCUBIN: %s", rtc.GetErrorString(rc));
+  *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return B200FFT_OK;
+}
+
+std::mutex g_jit_mutex;
+std::map<std::string, std::shared_ptr<JitKernel>>& cache() {
+  static std::map<std::string, std::shared_ptr<JitKernel>> c;  // key = device ordinal + spec key; modules live until exit
+  return c;
+}
+
+// compiled + loaded kernel for `spec` on `device` (the current device), from the cache when it was built before
+std::shared_ptr<JitKernel> get_kernel(const JitSpec& spec, int device) {
+  const Driver& drv = driver();
+  if (!drv.ok) {
+    fail(B200FFT_ERR_UNSUPPORTED, "driver entry points for module loading are unavailable");
+    return nullptr;
+  }
+  const std::string key = std::to_string(device) + "|" + spec.key();
+  std::lock_guard<std::mutex> lock(g_jit_mutex);
+  auto it = cache().find(key);
+  if (it != cache().end()) return it->second;
+  std::vector<char> cubin;
+  std::string lowered, log;
+  double ms = 0;
+  if (compile(spec, &cubin, &lowered, &log, &ms) != B200FFT_OK) {
+    if (getenv("B200FFT_JIT_VERBOSE")) fprintf(stderr, "[b200fft jit] %s\n", last_error().c_str());
+    cache()[key] = nullptr;  // do not retry a failing compile on every plan
+    return nullptr;
+  }
+  auto k = std::make_shared<JitKernel>();
+  k->cubin_bytes = cubin.size();
+  k->compile_ms = ms;
+  cudaFree(0);  // make sure the primary context of the current device exists and is current
+  if (drv.ModuleLoadData(&k->module, cubin.data()) != CUDA_SUCCESS || drv.ModuleGetFunction(&k->fn, k->module, lowered.c_str()) != CUDA_SUCCESS) {
+    fail(B200FFT_ERR_CUDA, "cannot load the compiled module for %s", spec.expression().c_str());
+    if (k->module) drv.ModuleUnload(k->module);
+    cache()[key] = nullptr;
+    return nullptr;
+  }
+  {  // the instantiation's own idea of its dynamic shared memory must agree with the host mirror the tile was sized with
+    CUdeviceptr gp = 0;
+    size_t gb = 0;
+    unsigned long long reported = ~0ull;
+    if (drv.ModuleGetGlobal(&gp, &gb, k->module, "b200fft_jit_smem_bytes") != CUDA_SUCCESS || gb != sizeof reported ||
+        cudaMemcpy(&reported, reinterpret_cast<const void*>(gp), sizeof reported, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        reported != (unsigned long long)spec.smem()) {
+      cudaGetLastError();
+      fail(B200FFT_ERR_CUDA, "%s: module reports %llu B of shared memory, the planner computed %zu", spec.name().c_str(), reported,
+           spec.smem());
+      if (getenv("B200FFT_JIT_VERBOSE")) fprintf(stderr, "[b200fft jit] %s\n", last_error().c_str());
+      drv.ModuleUnload(k->module);
+      cache()[key] = nullptr;
+      return nullptr;
+    }
+  }
+  drv.FuncGetAttribute(&k->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, k->fn);
+  drv.FuncGetAttribute(&k->local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, k->fn);
+  const size_t smem = spec.smem();
+  if (smem > 48 * 1024 && drv.FuncSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) {
+    fail(B200FFT_ERR_CUDA, "cannot reserve %zu B of shared memory for %s", smem, spec.name().c_str());
+    drv.ModuleUnload(k->module);
+    cache()[key] = nullptr;
+    return nullptr;
+  }
+  if (getenv("B200FFT_JIT_VERBOSE"))
+    fprintf(stderr, "[b200fft jit] %s: %.0f ms, cubin %zu B, %d registers, %d B local\n", spec.expression().c_str(), ms, cubin.size(),
+            k->regs, k->local_bytes);
+  cache()[key] = k;
+  return k;
+}
+
+// Group the user's ordered stage list into super-stages (register codelets): products <= 32, fewest stages, balanced
+// (the longest-processing-time rule rt.cu uses); a prime base above 32 (the reference allows any prime, fft.mojo:83-104
+// lists up to 97) becomes a stage of its own, up to JIT_MAX_PRIME.
+constexpr int JIT_MAX_RADIX = 32;
+constexpr int JIT_MAX_PRIME = 64;
+constexpr int JIT_MAX_STAGES = 5;
+
+bool jit_group_cap(const std::vector<uint32_t>& ordered, int cap, std::vector<int>* out) {
+  std::vector<uint32_t> small;
+  std::vector<int> big;
+  for (uint32_t r : ordered) {
+    if (r > (uint32_t)JIT_MAX_PRIME) return false;
+    if (r > (uint32_t)cap) big.push_back((int)r);
+    else small.push_back(r);
+  }
+  std::sort(small.begin(), small.end(), [](uint32_t x, uint32_t y) { return x > y; });
+  for (int want = small.empty() ? 0 : 1; want + (int)big.size() <= JIT_MAX_STAGES; ++want) {
+    std::vector<long long> g((size_t)want, 1);
+    bool ok = true;
+    for (uint32_t b : small) {
+      int best = -1;
+      for (int i = 0; i < want; ++i)
+        if (g[i] * b <= cap && (best < 0 || g[i] < g[best])) best = i;
+      if (best < 0) { ok = false; break; }
+      g[best] *= b;
+    }
+    if (!ok) continue;
+    out->clear();
+    for (int b : big) out->push_back(b);
+    for (long long v : g)
+      if (v > 1) out->push_back((int)v);
+    std::sort(out->begin(), out->end(), [](int x, int y) { return x > y; });  // largest radix first
+    if (out->empty()) out->push_back(1);
+    return true;
+  }
+  return false;
+}
+
+// Codelets of radix <= 32 keep a butterfly in ~64 data registers; when that needs three or more exchanges-worth of
+// stages, codelets up to JIT_WIDE_RADIX are tried and kept if they save a stage (1000 = 10 x 10 x 10 -> 40 x 25: one
+// shared-memory exchange instead of two).   B200FFT_JIT_MAX_RADIX=<r> overrides the wide cap (A/B knob).
+constexpr int JIT_WIDE_RADIX = 50;
+bool jit_group(const std::vector<uint32_t>& ordered, std::vector<int>* out) {
+  if (!jit_group_cap(ordered, JIT_MAX_RADIX, out)) return false;
+  int wide = JIT_WIDE_RADIX;
+  if (const char* e = getenv("B200FFT_JIT_MAX_RADIX")) wide = std::max(2, std::min(64, atoi(e)));
+  if (out->size() >= 3 && wide > JIT_MAX_RADIX) {
+    std::vector<int> w;
+    if (jit_group_cap(ordered, wide, &w) && w.size() < out->size()) *out = w;
+  }
+  return true;
+}
+
+// Tile shape and CTA size, following the hand-tuned variants (fast_reg_*.cu): about one thread per butterfly of the
+// stage with the LARGEST radix (fewest butterflies; up to four rounds when that would be too many threads), tiles of
+// 16-48 KB so several CTAs share an SM, strided tiles 16 columns wide (128 contiguous bytes per axis step) unless the
+// axis is so long that only 8 fit. Every candidate (tile, rounds) is scored; the cheapest wins.
+bool jit_geometry(JitSpec* s, long long inner) {
+  const int rmax = *std::max_element(s->radices.begin(), s->radices.end());
+  const int rlast = s->radices.back();
+  const long long per = (long long)s->n / rmax;  // butterflies of the widest stage per sub-transform
+  std::vector<int> tiles;
+  if (s->strided()) {
+    for (int t : {8, 16, 32, 64})
+      if (t <= std::max<long long>(8, (inner + 7) / 8 * 8)) tiles.push_back(t);
+    if (inner < 8) tiles.assign(1, (int)inner);
+  } else {
+    for (int t = 1; t <= 256; ++t) tiles.push_back(t);
+  }
+  double best = 1e30;
+  int best_tile = 0, best_nt = 0;
+  for (int tile : tiles) {
+    s->tile = tile;
+    const size_t smem = s->smem();
+    if (smem > 200 * 1024) continue;
+    if (s->kind == JIT_R2C_REG && ((long long)tile * (s->n / rlast)) % 32 != 0) continue;  // r2c_reg_ok(): whole warps per row group
+    const long long work = tile * per;
+    const double bytes = (double)tile * s->n * 8;
+    for (int rounds = 1; rounds <= 4; ++rounds) {
+      long long nt = ((work + rounds - 1) / rounds + 31) / 32 * 32;
+      if (nt < 64 && rounds > 1) continue;
+      if (nt < 32 || nt > 512) continue;
+      const double waste = (double)(nt * rounds - work) / (double)(nt * rounds);
+      double score = 4.0 * waste + 0.5 * std::fabs(std::log2(bytes / 32768.0)) + 0.3 * std::fabs(std::log2((double)nt / 256.0)) +
+                     0.15 * (rounds - 1) + (smem > 64 * 1024 ? 0.5 : 0.0);
+      if (s->strided() && tile < 16) score += 0.6;  // 64-byte runs: only when nothing wider fits
+      if (score < best) {
+        best = score;
+        best_tile = tile;
+        best_nt = (int)nt;
+      }
+    }
+  }
+  if (!best_tile) return false;
+  s->tile = best_tile;
+  s->threads = best_nt;
+  return s->smem() <= 227 * 1024;
+}
+
+// rows_r2c_reg_kernel's precondition (fast.cuh: r2c_reg_ok) apart from the tile, which jit_geometry picks
+bool r2c_reg_shape_ok(const JitSpec& s) {
+  const int P = s.n / s.radices.back();
+  return s.radices.size() >= 1 && P >= 8 && P <= 32 && 32 % P == 0;
+}
+
+struct JitPass : Pass {
+  JitSpec spec;
+  std::shared_ptr<JitKernel> k;
+  std::shared_ptr<JitKernel> k_scatter;  // compiled on the first launch_scatter
+  AxisView view;
+  int device = 0;
+  bool do_scale = false;
+  float scale = 1.f;
+  float2* d_tw = nullptr;
+  float2* d_tw2 = nullptr;  // W_n^{+-k} of the Hermitian unpack / pack
+  size_t smem = 0;
+  std::string text;
+
+  int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) override {
+    return launch_outer(src, dst, nbatch * view.outer_per_batch, stream);
+  }
+  bool supports_units() const override { return true; }
+  int launch_units(const void* src, void* dst, int64_t nunits, int64_t units_per_batch, cudaStream_t stream) override {
+    if (units_per_batch < 1 || view.outer_per_batch % units_per_batch)
+      return fail(B200FFT_ERR_INVALID_ARG, "%s: outer slabs do not split into %lld units", text.c_str(), (long long)units_per_batch);
+    return launch_outer(src, dst, nunits * (view.outer_per_batch / units_per_batch), stream);
+  }
+  int run(const JitKernel& kern, const JitSpec& sp, long long grid, void** params, cudaStream_t stream) {
+    if (grid <= 0) return B200FFT_OK;
+    if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many tiles");
+    const CUresult r = driver().LaunchKernel(kern.fn, (unsigned)grid, 1, 1, (unsigned)sp.threads, 1, 1, (unsigned)sp.smem(),
+                                             (CUstream)stream, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(B200FFT_ERR_CUDA, "launch of %s failed (CUresult %d)", sp.name().c_str(), (int)r);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return B200FFT_OK;
+  }
+  ColsArgs cols_args(const void* src, void* dst) const {
+    ColsArgs ca;
+    ca.in = src;
+    ca.out = reinterpret_cast<float2*>(dst);
+    ca.tw = d_tw;
+    ca.inner = view.inner;
+    ca.tiles_per_outer = (int)((view.inner + spec.tile - 1) / spec.tile);
+    ca.scale = scale;
+    ca.do_scale = do_scale;
+    return ca;
+  }
+  int launch_outer(const void* src, void* dst, int64_t outer, cudaStream_t stream) {
+    void* params[1];
+    if (spec.kind == JIT_ROWS) {
+      RowsArgs ra;
+      ra.in = src;
+      ra.out = reinterpret_cast<float2*>(dst);
+      ra.tw = d_tw;
+      ra.nrows = outer;
+      ra.scale = scale;
+      ra.do_scale = do_scale;
+      params[0] = &ra;
+      return run(*k, spec, (outer + spec.tile - 1) / spec.tile, params, stream);
+    }
+    if (spec.kind == JIT_COLS) {
+      ColsArgs ca = cols_args(src, dst);
+      params[0] = &ca;
+      return run(*k, spec, outer * ca.tiles_per_outer, params, stream);
+    }
+    HalfArgs ha;  // the half-spectrum row kernels
+    ha.in = src;
+    ha.out = dst;
+    ha.tw = d_tw;
+    ha.tw2 = d_tw2;
+    ha.nrows = outer;
+    ha.scale = scale;
+    params[0] = &ha;
+    return run(*k, spec, (outer + spec.tile - 1) / spec.tile, params, stream);
+  }
+  int launch_scatter(const void* src, const Scatter& sc, int64_t nbatch, cudaStream_t stream) override {
+    if (spec.kind != JIT_COLS || spec.real_in) return fail(B200FFT_ERR_UNSUPPORTED, "no scattering store for %s", text.c_str());
+    if (sc.npeers < 1 || sc.npeers > 16 || view.n % sc.npeers)
+      return fail(B200FFT_ERR_INVALID_ARG, "split axis length %lld is not divisible by %d peers", (long long)view.n, sc.npeers);
+    JitSpec sp = spec;
+    sp.kind = JIT_SCATTER;
+    if (!k_scatter) {
+      int cur = -1;
+      cudaGetDevice(&cur);
+      if (cur != device) cudaSetDevice(device);
+      k_scatter = get_kernel(sp, device);
+      if (cur != device && cur >= 0) cudaSetDevice(cur);
+      if (!k_scatter) return fail(B200FFT_ERR_UNSUPPORTED, "could not specialise the scattering store for %s", text.c_str());
+    }
+    ColsArgs ca = cols_args(src, nullptr);
+    ScatterArgs sa;
+    for (int i = 0; i < 16; ++i) sa.peer[i] = i < sc.npeers ? reinterpret_cast<float2*>(sc.peer_out[i]) : nullptr;
+    sa.yl = (int)(view.n / sc.npeers);
+    const long long outer = nbatch * view.outer_per_batch;
+    sa.zbase = (long long)sc.my_rank * outer;
+    void* params[2] = {&ca, &sa};
+    return run(*k_scatter, sp, outer * ca.tiles_per_outer, params, stream);
+  }
+  std::string describe() const override { return text; }
+};
+
+bool jit_enabled() {
+  const char* e = getenv("B200FFT_JIT");
+  return !(e && atoi(e) == 0);
+}
+
+// kind + transform length + stage list for one axis; false when this tier does not serve it
+bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, bool inverse, HalfMode half, JitSpec* spec) {
+  spec->inverse = inverse;
+  spec->real_in = src.comps == 1;
+  if (half == HALF_NONE) {
+    spec->kind = view.inner != 1 ? JIT_COLS : JIT_ROWS;
+    spec->n = (int)view.n;
+    if (!jit_group(ax.ordered, &spec->radices)) return false;
+  } else {
+    if (view.inner != 1) return false;  // half-spectrum handling is a row pass
+    if (view.n % 2) {
+      if (half != HALF_R2C) return false;  // C2R of odd lengths stays on the runtime-length tier
+      spec->kind = JIT_R2C_ODD;
+      spec->n = (int)view.n;
+      if (!jit_group(ax.ordered, &spec->radices)) return false;
+    } else {
+      // n = 2H real points as an H-point complex transform: the user's stage list with one factor 2 removed
+      spec->n = (int)(view.n / 2);
+      bool ok = false;
+      for (const auto& o : drop_factor_two(ax.ordered))
+        if (jit_group(o, &spec->radices)) { ok = true; break; }
+      if (!ok) return false;
+      if (spec->n == 1) return false;
+      spec->kind = half == HALF_C2R ? JIT_C2R : JIT_R2C;
+      if (half == HALF_R2C && r2c_reg_shape_ok(*spec) && !getenv("B200FFT_R2C_SMEM")) spec->kind = JIT_R2C_REG;
+    }
+    spec->inverse = half == HALF_C2R;
+    spec->real_in = false;
+  }
+  // packed FADD2 adds: the measured win for mixed-radix and strided kernels, a loss for contiguous power-of-two rows
+  // (dft.cuh, profiles/r1_packed_fadd2.md)
+  spec->packed = spec->strided() || (spec->n & (spec->n - 1)) != 0;
+  if (!jit_geometry(spec, view.inner)) {
+    if (spec->kind != JIT_R2C_REG) return false;
+    spec->kind = JIT_R2C;  // no tile keeps whole warps per row group: the shared-memory unpack
+    if (!jit_geometry(spec, view.inner)) return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src, bool scale_inverse,
+                                    HalfMode half) {
+  const Problem& p = plan.prob;
+  if (!jit_enabled()) return nullptr;
+  if (p.desc.out_dtype != B200FFT_F32 || src.dtype != B200FFT_F32 || view.n > 16384 || view.n < 2) return nullptr;
+  JitSpec spec;
+  if (!jit_plan_axis(p.axes[axis], view, src, p.desc.inverse != 0, half, &spec)) return nullptr;
+  std::shared_ptr<JitKernel> k = get_kernel(spec, plan.device);
+  if (!k) return nullptr;
+  auto pass = std::make_unique<JitPass>();
+  pass->spec = spec;
+  pass->k = k;
+  pass->view = view;
+  pass->device = plan.device;
+  pass->do_scale = scale_inverse;
+  pass->scale = scale_inverse ? (float)(1.0 / (double)view.n) : 1.f;
+  if (half == HALF_C2R) pass->scale = (float)(1.0 / (double)view.n);  // the half-spectrum inverse is always normalised
+  pass->smem = spec.smem();
+  auto upload = [&](const std::vector<float2>& t, float2** d) {
+    if (cudaMalloc(d, t.size() * sizeof(float2)) != cudaSuccess) { cudaGetLastError(); return false; }
+    plan.owned_device.push_back(*d);  // owned by the plan before the copy: a failed copy must not leak it
+    return cudaMemcpy(*d, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  if (!upload(build_twiddles(spec.radices, spec.inverse), &pass->d_tw)) return nullptr;
+  if (half != HALF_NONE && spec.kind != JIT_R2C_ODD && !upload(build_half_twiddles(view.n, half == HALF_C2R), &pass->d_tw2))
+    return nullptr;
+  std::string stages;
+  for (uint32_t r : p.axes[axis].ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
+  char buf[400];
+  snprintf(buf, sizeof buf, "axis %d: %s n=%lld inner=%lld smem=%zuB regs=%d user stages=[%s] fused as %s(%s)%s [NVRTC, %.0f ms]", axis,
+           spec.name().c_str(), (long long)view.n, (long long)view.inner, pass->smem, k->regs, stages.c_str(),
+           half != HALF_NONE && spec.kind != JIT_R2C_ODD ? "(2)" : "", radix_name(spec.radices).c_str(),
+           half == HALF_R2C ? (spec.kind == JIT_R2C_ODD ? " r2c (real rows, bins 0..n/2 stored)" : " r2c")
+           : half == HALF_C2R ? " c2r" : spec.real_in ? " real-in" : "",
+           k->compile_ms);
+  pass->text = buf;
+  return pass;
+}
+
+// Host-only probe (no CUDA device needed): compile the kernel the planner would pick for one axis and report it.
+// half: 0 = complex / real-input full spectrum, 1 = R2C rows, 2 = C2R rows
+int jit_probe(int64_t n, int64_t inner, const std::vector<uint32_t>& ordered, bool inverse, bool real_in, int half,
+              std::string* report) {
+  AxisSpec ax;
+  ax.n = n;
+  ax.ordered = ordered;
+  AxisView view;
+  view.n = n;
+  view.inner = inner;
+  IoSpec src;
+  src.comps = real_in ? 1 : 2;
+  JitSpec spec;
+  if (!jit_plan_axis(ax, view, src, inverse, (HalfMode)half, &spec))
+    return fail(B200FFT_ERR_UNSUPPORTED, "the specialisation tier does not serve this axis (radix above %d, or no tile fits)", JIT_MAX_PRIME);
+  std::vector<char> cubin;
+  std::string lowered, log;
+  double ms = 0;
+  const int rc = compile(spec, &cubin, &lowered, &log, &ms);
+  if (rc != B200FFT_OK) return rc;
+  char buf[640];
+  snprintf(buf, sizeof buf, "%s: %s, smem=%zuB, cubin=%zuB, %.0f ms, symbol %s", spec.name().c_str(), spec.expression().c_str(), spec.smem(),
+           cubin.size(), ms, lowered.c_str());
+  *report = buf;
+  return B200FFT_OK;
+}
+
+}  // namespace b200fft

@@ -113,6 +113,11 @@ std::unique_ptr<Pass> make_rt_pass(b200fft_plan& plan, int axis, const AxisView&
                                    bool scale_inverse, HalfMode half = HALF_NONE);
 // fused N-d kernel (fused_registry.cu): one pass object that replaces ALL per-axis passes, or nullptr
 std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan);
+// plan-time specialisation (jit.cu): the compile-time kernels instantiated through NVRTC for unregistered lengths
+std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src, bool scale_inverse,
+                                    HalfMode half);
+int jit_probe(int64_t n, int64_t inner, const std::vector<uint32_t>& ordered, bool inverse, bool real_in, int half,
+              std::string* report);
 // number of registered kernel variants per tier (host-only; triggers the one-time registration)
 size_t fast_variant_count();
 size_t fused_variant_count();

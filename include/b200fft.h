@@ -237,6 +237,14 @@ B200FFT_API int b200fft_default_bases(uint64_t length, int gpu_target, uint32_t*
 /* validate a descriptor and write the pass list it would produce, without touching CUDA */
 B200FFT_API int b200fft_plan_dry_run(const b200fft_desc* desc, char* buf, size_t cap);
 
+/* Plan-time specialisation (csrc/jit.cu): axis lengths without a hand-registered kernel variant get the compile-time
+ * kernels instantiated through NVRTC when the plan is created — the run-time counterpart of the reference
+ * specialising every (length, bases) at compile time (_ndim_fft_gpu.mojo:279-450). This probe compiles the kernel the
+ * planner would pick for ONE axis (length n, element stride `inner`, user bases or NULL for the default rule) and
+ * writes "<variant>: <template-id>, smem, cubin size, compile time, symbol" into buf. Needs libnvrtc but no GPU. */
+B200FFT_API int b200fft_jit_probe(int64_t n, int64_t inner, const uint32_t* bases, int nbases, int inverse, int real_in,
+                                  int half /* 0 complex, 1 half-spectrum R2C rows, 2 C2R rows */, char* buf, size_t cap);
+
 /* Tile schedule of the fused N-d kernel (host logic, no CUDA): phases[p] = {tiles_per_transform,
  * tiles_per_group, dep_div, quota}; writes up to `cap` segments as {phase, first_item, first_tile, count}
  * and returns the number of segments (or -1). Tests use it to check that every tile appears once and

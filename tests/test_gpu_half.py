@@ -137,10 +137,13 @@ def test_f64_and_errors():
     assert e.value.status == 2
 
 
-def test_unregistered_lengths_use_the_rt_tier():
-    """Half-spectrum rows without a fused R2C/C2R kernel run on the runtime-length tier (n-point transform, bins
-    0..n/2 stored / Hermitian-extended load), not on the generic kernel; an odd length with a registered row variant
-    (93 = 31 x 3) runs its R2C on that compile-time kernel with a half-bins store (C2R of odd n stays on the rt tier)."""
+def test_unregistered_lengths_use_the_rt_tier(monkeypatch):
+    """Half-spectrum rows without a registered R2C/C2R kernel: with the plan-time specialisation tier switched off
+    (B200FFT_JIT=0; with it on they get an NVRTC-built R2C kernel, tests/test_gpu_jit.py) they run on the runtime-length
+    tier (n-point transform, bins 0..n/2 stored / Hermitian-extended load), not on the generic kernel; an odd length with
+    a registered row variant (93 = 31 x 3) runs its R2C on that compile-time kernel with a half-bins store (C2R of odd n
+    stays on the rt tier)."""
+    monkeypatch.setenv("B200FFT_JIT", "0")
     rng = np.random.default_rng(4)
     for shape, kernel in (((6, 93), "r2c-odd[rows93"), ((3, 1000), "rt_rows"), ((2, 12, 30), "rt_rows"),
                           ((2, 20, 93), "r2c-odd[rows93")):

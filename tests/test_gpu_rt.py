@@ -38,7 +38,8 @@ def test_rt_tier(oracle, shape, bases, inverse, in_dtype, comps):
     rng = np.random.default_rng(17)
     full = shape + (comps,)
     x = rng.integers(0, 256, size=full).astype(np.uint8) if in_dtype == "uint8" else rng.standard_normal(full).astype(in_dtype)
-    plan = b200fft.plan_fft(in_dtype, "float32", full, shape + (2,), bases=bases, inverse=inverse)
+    # FORCE_RT: without it these lengths get a kernel specialised at plan time (csrc/jit.cu, tests/test_gpu_jit.py)
+    plan = b200fft.plan_fft(in_dtype, "float32", full, shape + (2,), bases=bases, inverse=inverse, flags=b200fft.FLAG_FORCE_RT)
     desc = plan.describe()
     assert "rt_" in desc and "generic" not in desc, desc
     out = torch.full(shape + (2,), float("nan"), device="cuda")
@@ -58,8 +59,10 @@ def test_rt_tier(oracle, shape, bases, inverse, in_dtype, comps):
     plan.destroy()
 
 
-def test_radix_above_32_stays_generic():
-    p = b200fft.plan_fft("float32", "float32", (4, 74, 2), (4, 74, 2))      # 74 = 37 * 2
+def test_radix_above_64_stays_generic():
+    p = b200fft.plan_fft("float32", "float32", (4, 74, 2), (4, 74, 2), flags=b200fft.FLAG_FORCE_RT)   # 74 = 37 * 2
+    assert "generic" in p.describe()                                      # the rt tier's codelets stop at radix 32
+    p = b200fft.plan_fft("float32", "float32", (4, 134, 2), (4, 134, 2))    # 134 = 67 * 2: above the JIT tier's limit too
     assert "generic" in p.describe()
     p = b200fft.plan_fft("float32", "float32", (4, 64, 2), (4, 64, 2), _test="generic")
     assert "generic" in p.describe()
@@ -71,7 +74,7 @@ def test_rt_is_much_faster_than_generic():
     out = torch.empty_like(x)
     st = torch.cuda.current_stream().cuda_stream
     times = {}
-    for name, kw in (("rt", {}), ("generic", {"_test": "generic"})):
+    for name, kw in (("rt", {"flags": b200fft.FLAG_FORCE_RT}), ("generic", {"_test": "generic"})):
         plan = b200fft.plan_fft("float32", "float32", x.shape, x.shape, **kw)
         for _ in range(3):
             plan.exec(out, x, st)

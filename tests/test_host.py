@@ -263,3 +263,20 @@ def test_mgpu_needs_cuda_no_fallback():
     with pytest.raises(b200fft.B200FFTError) as e:
         b200fft.MgpuPlan("float32", "float32", (8, 64, 2), (8, 64, 2), devices=[0])
     assert e.value.status == 5
+
+
+def test_jit_sources_compile_with_nvrtc_for_sm100a():
+    """The plan-time specialisation tier's sources (the device headers embedded in the library) compile for sm_100a
+    with NVRTC in this container: rows and strided kernels, forward / inverse, real input, a prime radix above 32."""
+    for kw, want in ((dict(n=1000), "rows_kernel<1000, b200fft::Radices<10, 10, 10>"),
+                     (dict(n=360, inner=360, inverse=True), "cols_kernel<360, b200fft::Radices<20, 18>, 16, 288, true, false>"),
+                     (dict(n=200, real_in=True), "false, true>"),
+                     (dict(n=74), "Radices<37, 2>")):
+        rep = b200fft.jit_probe(**kw)
+        assert want in rep and "cubin=" in rep, rep
+    with pytest.raises(b200fft.B200FFTError) as e:
+        b200fft.jit_probe(n=134)                       # 67 x 2: left to the generic kernel
+    assert e.value.status == 4
+    with pytest.raises(b200fft.B200FFTError) as e:
+        b200fft.jit_probe(n=100, bases=[3])
+    assert e.value.status == 3

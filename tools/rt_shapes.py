@@ -10,6 +10,8 @@ from bench import CuFFT, time_gpu, measured_peak
 
 SHAPES = [(200000, 100), (50000, 1000), (100000, 243), (20000, 2000), (4000, 10000), (200, 300, 300), (20, 1000, 1000),
           (50, 100, 100, 100), (4, 200, 200, 200), (100000, 210)]
+if os.environ.get("RT_SHAPES"):   # e.g. RT_SHAPES="50000x1000;20x1000x1000"
+    SHAPES = [tuple(int(v) for v in t.split("x")) for t in os.environ["RT_SHAPES"].split(";")]
 peak, _ = measured_peak()
 st = torch.cuda.current_stream().cuda_stream
 for shape in SHAPES:
