@@ -268,7 +268,10 @@ def test_mgpu_needs_cuda_no_fallback():
 def test_jit_sources_compile_with_nvrtc_for_sm100a():
     """The plan-time specialisation tier's sources (the device headers embedded in the library) compile for sm_100a
     with NVRTC in this container: rows and strided kernels, forward / inverse, real input, a prime radix above 32."""
-    for kw, want in ((dict(n=1000), "rows_kernel<1000, b200fft::Radices<10, 10, 10>"),
+    for kw, want in ((dict(n=1000), "rows_kernel<1000, b200fft::Radices<40, 25>"),      # wide codelets save a stage
+                     (dict(n=1000, half=1), "rows_r2c_kernel<500, b200fft::Radices<25, 20>"),
+                     (dict(n=1000, half=2), "rows_c2r_kernel<500, b200fft::Radices<25, 20>"),
+                     (dict(n=243, half=1), "rows_r2c_odd_kernel<243, b200fft::Radices<27, 9>"),
                      (dict(n=360, inner=360, inverse=True), "cols_kernel<360, b200fft::Radices<20, 18>, 16, 288, true, false>"),
                      (dict(n=200, real_in=True), "false, true>"),
                      (dict(n=74), "Radices<37, 2>")):
