@@ -286,7 +286,9 @@ int b200fft_default_bases(uint64_t length, int gpu_target, uint32_t* out, int ca
 }
 
 int b200fft_jit_probe(int64_t n, int64_t inner, const uint32_t* bases, int nbases, int inverse, int real_in, int half,
-                      char* buf, size_t cap) {
+                      int in_dtype, int out_dtype, char* buf, size_t cap) {
+  if (in_dtype < B200FFT_U8 || in_dtype > B200FFT_F64 || (out_dtype != B200FFT_F32 && out_dtype != B200FFT_F64))
+    return fail(B200FFT_ERR_INVALID_ARG, "dtypes %d -> %d", in_dtype, out_dtype);
   if (half < 0 || half > 2) return fail(B200FFT_ERR_INVALID_ARG, "half = %d (0 complex, 1 R2C, 2 C2R)", half);
   if (n < 2 || inner < 1) return fail(B200FFT_ERR_INVALID_ARG, "axis length %lld, inner %lld", (long long)n, (long long)inner);
   std::vector<uint32_t> ordered;
@@ -297,7 +299,7 @@ int b200fft_jit_probe(int64_t n, int64_t inner, const uint32_t* bases, int nbase
   }
   if (!ordered_bases_valid((uint64_t)n, ordered)) return fail(B200FFT_ERR_BASES, "bases do not factor %lld", (long long)n);
   std::string report;
-  const int rc = jit_probe(n, inner, ordered, inverse != 0, real_in != 0, half, &report);
+  const int rc = jit_probe(n, inner, ordered, inverse != 0, real_in != 0, half, in_dtype, out_dtype, &report);
   if (rc != B200FFT_OK) return rc;
   if (buf && cap) {
     strncpy(buf, report.c_str(), cap - 1);

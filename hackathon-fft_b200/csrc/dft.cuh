@@ -141,7 +141,7 @@ B200_HD float2 twiddle_mul(float2 a) {
     return rot90<!INV>(a);
   } else if constexpr ((8 * k) % N == 0) {
     // odd multiples of 1/8 turn: (+-1 +- i)/sqrt(2)
-    constexpr float h = 0.70710678118654752440f;
+    constexpr float h = (float)0.70710678118654752440;
     constexpr float sr = Tw<k, N, INV>::re > 0 ? h : -h;
     constexpr float si = Tw<k, N, INV>::im > 0 ? h : -h;
     return make_float2(sr * a.x - si * a.y, si * a.x + sr * a.y);

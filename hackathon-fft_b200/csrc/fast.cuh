@@ -84,12 +84,15 @@ struct GlobalSrc {
   __device__ __forceinline__ float2 load(int o, int i, int c) const {
     if (o >= valid_o || c >= valid_c) return make_float2(0.f, 0.f);
     const long long idx = o * so + i * si + c;
+    // in_scalar / in_vec2: the input array's own element type (fp32 except in run-time specialised kernels that read
+    // a uint8 / fp64 array, rtc_prelude.cuh), cast to the working precision on load
     if constexpr (REAL) {
-      const float* p = reinterpret_cast<const float*>(base) + idx;
-      return make_float2(COHERENT ? __ldcg(p) : __ldg(p), 0.f);
+      const in_scalar* p = reinterpret_cast<const in_scalar*>(base) + idx;
+      return make_float2((float)(COHERENT ? __ldcg(p) : __ldg(p)), 0.f);
     } else {
-      const float2* p = reinterpret_cast<const float2*>(base) + idx;
-      return COHERENT ? __ldcg(p) : __ldg(p);
+      const in_vec2* p = reinterpret_cast<const in_vec2*>(base) + idx;
+      const in_vec2 v = COHERENT ? __ldcg(p) : __ldg(p);
+      return make_float2((float)v.x, (float)v.y);
     }
   }
 };
@@ -114,7 +117,11 @@ struct GlobalSrcV4 {
   int valid_o;
   __device__ __forceinline__ float4 load2(int o, int i_even) const {
     if (o >= valid_o) return make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef B200FFT_JIT_F64  // never instantiated in fp64 builds (VEC is an fp32 option); there is no 32-byte __ldg
+    return *reinterpret_cast<const float4*>(base + o * so + i_even);
+#else
     return __ldg(reinterpret_cast<const float4*>(base + o * so + i_even));
+#endif
   }
 };
 struct GlobalDstV4 {
@@ -162,6 +169,7 @@ __device__ __forceinline__ void tile_sync() {
 // TWS: `tw` points into shared memory (persistent kernels stage their tables once per CTA)
 template <bool TWS>
 __device__ __forceinline__ float2 tw_load(const float2* tw, int idx) {
+#ifndef B200FFT_JIT_F64  // (the persistent kernels that keep their tables in shared memory are fp32 only)
   if constexpr (TWS) {
     float2 v;
     // volatile + memory clobber: the table is written by other threads of the CTA before a barrier; the
@@ -171,9 +179,9 @@ __device__ __forceinline__ float2 tw_load(const float2* tw, int idx) {
                  : "r"((unsigned)__cvta_generic_to_shared(tw + idx))
                  : "memory");
     return v;
-  } else {
-    return __ldg(tw + idx);
   }
+#endif
+  return __ldg(tw + idx);
 }
 
 template <int R, int P, int N, int O, int CN, int NT, bool INV, bool TWS = false, class Src, class Dst>
@@ -319,8 +327,8 @@ __global__ void __launch_bounds__(NT) rows_kernel(const __grid_constant__ RowsAr
   float2* buf1 = smem_f2 + BUF;
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
-  const void* in = REAL ? (const void*)(reinterpret_cast<const float*>(a.in) + row0 * N)
-                        : (const void*)(reinterpret_cast<const float2*>(a.in) + row0 * N);
+  const void* in = REAL ? (const void*)(reinterpret_cast<const in_scalar*>(a.in) + row0 * N)
+                        : (const void*)(reinterpret_cast<const in_vec2*>(a.in) + row0 * N);
   if constexpr (VEC && !REAL) {
     GlobalSrcV4 src{reinterpret_cast<const float2*>(a.in) + row0 * N, N, valid};
     GlobalDstV4 dst{a.out + row0 * N, N, valid};
@@ -453,7 +461,7 @@ __device__ __forceinline__ void r2c_tile_from(const Src& src, float2* __restrict
   }
 }
 template <int H, class RL, int C, int NT, bool COHERENT = false>
-__device__ __forceinline__ void r2c_tile(const float2* in, float2* __restrict__ out, const float2* __restrict__ tw,
+__device__ __forceinline__ void r2c_tile(const in_vec2* in, float2* __restrict__ out, const float2* __restrict__ tw,
                                          const float2* __restrict__ tw2, int valid, float2* smem_f2) {
   GlobalSrc<false, COHERENT> src{in, H, 1, valid, 1};
   r2c_tile_from<H, RL, C, NT, false>(src, out, tw, tw2, valid, smem_f2, [] {});
@@ -464,7 +472,7 @@ __global__ void __launch_bounds__(NT) rows_r2c_kernel(const __grid_constant__ Ha
   extern __shared__ __align__(16) float2 smem_f2[];
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
-  r2c_tile<H, RL, C, NT>(reinterpret_cast<const float2*>(a.in) + row0 * H,
+  r2c_tile<H, RL, C, NT>(reinterpret_cast<const in_vec2*>(a.in) + row0 * H,
                          reinterpret_cast<float2*>(a.out) + row0 * (H + 1), a.tw, a.tw2, valid, smem_f2);
 }
 
@@ -524,7 +532,7 @@ __global__ void __launch_bounds__(NT) rows_r2c_reg_kernel(const __grid_constant_
   constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
-  GlobalSrc<false> src{reinterpret_cast<const float2*>(a.in) + row0 * H, H, 1, valid, 1};
+  GlobalSrc<false> src{reinterpret_cast<const in_vec2*>(a.in) + row0 * H, H, 1, valid, 1};
   R2CRegDst<H> dst{reinterpret_cast<float2*>(a.out) + row0 * (H + 1), a.tw2, valid};
   run_axis<RL, H, C, 1, NT, false, RowLayoutN<H>::template type>(src, dst, smem_f2, smem_f2 + EX, a.tw, 1.f, false);
 }
@@ -547,7 +555,7 @@ __global__ void __launch_bounds__(NT) rows_r2c_odd_kernel(const __grid_constant_
   constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
-  GlobalSrc<true> src{reinterpret_cast<const float*>(a.in) + row0 * N, N, 1, valid, 1};
+  GlobalSrc<true> src{reinterpret_cast<const in_scalar*>(a.in) + row0 * N, N, 1, valid, 1};
   GlobalHalfDst dst{reinterpret_cast<float2*>(a.out) + row0 * (N / 2 + 1), N / 2 + 1, valid};
   run_axis<RL, N, C, 1, NT, false, RowLayoutN<N>::template type>(src, dst, smem_f2, smem_f2 + BUF, a.tw, 1.f, false);
 }
@@ -576,9 +584,15 @@ __global__ void __launch_bounds__(NT) rows_c2r_kernel(const __grid_constant__ Ha
   float2* xbuf = smem_f2 + 2 * EX;  // [C][H+1]
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
-  const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + row0 * (H + 1);
-  for (int idx = threadIdx.x; idx < C * (H + 1); idx += NT)
-    xbuf[idx] = idx < valid * (H + 1) ? __ldg(&in[idx]) : make_float2(0.f, 0.f);
+  const in_vec2* __restrict__ in = reinterpret_cast<const in_vec2*>(a.in) + row0 * (H + 1);
+  for (int idx = threadIdx.x; idx < C * (H + 1); idx += NT) {
+    float2 v = make_float2(0.f, 0.f);
+    if (idx < valid * (H + 1)) {
+      const in_vec2 w = __ldg(&in[idx]);
+      v = make_float2((float)w.x, (float)w.y);
+    }
+    xbuf[idx] = v;
+  }
   __syncthreads();
   GlobalDst dst{reinterpret_cast<float2*>(a.out) + row0 * H, H, 1, valid, 1};
   run_axis<RL, H, C, 1, NT, true, RowLayoutN<H>::template type>(HermSrc<H>{xbuf, a.tw2}, dst, buf0, buf1, a.tw, a.scale,
@@ -617,8 +631,8 @@ __global__ void __launch_bounds__(NT) cols_kernel(const __grid_constant__ ColsAr
   const long long c0 = (long long)(blockIdx.x - o * a.tiles_per_outer) * CW;
   const long long base = o * N * a.inner + c0;
   const int valid_c = (int)min((long long)CW, a.inner - c0);
-  const void* in = REAL ? (const void*)(reinterpret_cast<const float*>(a.in) + base)
-                        : (const void*)(reinterpret_cast<const float2*>(a.in) + base);
+  const void* in = REAL ? (const void*)(reinterpret_cast<const in_scalar*>(a.in) + base)
+                        : (const void*)(reinterpret_cast<const in_vec2*>(a.in) + base);
   GlobalSrc<REAL> src{in, 0, a.inner, 1, valid_c};
   GlobalDst dst{a.out + base, 0, a.inner, 1, valid_c};
   run_axis<RL, N, 1, CW, NT, INV, DenseLayoutN<N, CW>::template type>(src, dst, buf0, buf1, a.tw, a.scale,

@@ -139,7 +139,10 @@ struct JitSpec {
   std::vector<int> radices;
   int tile = 0, threads = 0;
   bool inverse = false, real_in = false, packed = false;
+  bool f64 = false;            // working precision (the plan's out_dtype): fp64 = the same kernels with the scalar type swapped
+  int in_dtype = B200FFT_F32;  // element type of the array the kernel READS (cast on load)
 
+  size_t esz() const { return f64 ? sizeof(double2) : sizeof(float2); }
   bool strided() const { return kind == JIT_COLS || kind == JIT_SCATTER; }
   std::string radix_list() const {
     std::string s;
@@ -177,9 +180,17 @@ struct JitSpec {
   std::string name() const {
     static const char* const tag[] = {"jitrows", "jitcols", "jitscatter", "jitr2c", "jitr2creg", "jitr2codd", "jitc2r"};
     return std::string(tag[kind]) + std::to_string(n) + "_" + radix_name(radices) + (strided() ? "_w" : "_c") + std::to_string(tile) +
-           "_t" + std::to_string(threads);
+           "_t" + std::to_string(threads) + (f64 ? "_f64" : "") + (in_dtype == B200FFT_U8 ? "_inu8" : in_dtype == (f64 ? B200FFT_F32 : B200FFT_F64) ? (f64 ? "_inf32" : "_inf64") : "");
   }
-  std::string key() const { return expression() + (packed ? "|p" : "|s"); }
+  std::string defines() const {  // rtc_prelude.cuh reads these
+    std::string d;
+    if (in_dtype == B200FFT_U8) d += "#define B200FFT_JIT_IN_U8 1\n";
+    if (in_dtype == B200FFT_F64) d += "#define B200FFT_JIT_IN_F64 1\n";
+    if (f64) d += "#define B200FFT_JIT_F64 1\n";
+    if (packed && !f64) d += "#define B200FFT_PACKED 1\n";
+    return d;
+  }
+  std::string key() const { return expression() + "|" + defines(); }
   // Host mirror of the smem_expression() formulas (fast.cuh): used to choose the tile before anything is compiled, and
   // checked against the value the compiled module reports (b200fft_jit_smem_bytes) when it is loaded.
   // RowLayout pads a Q-block by P elements when P < 16, Q even and Q < N; DenseLayout is N x CW.
@@ -199,9 +210,9 @@ struct JitSpec {
     }
     const size_t pingpong = radices.size() > 2 ? 2 : 1;
     switch (kind) {
-      case JIT_R2C: return sizeof(float2) * (size_t)std::max<long long>(ex, (long long)tile * n) * 2;
-      case JIT_C2R: return sizeof(float2) * ((size_t)ex * 2 + (size_t)tile * (n + 1));
-      default: return sizeof(float2) * (size_t)ex * pingpong;
+      case JIT_R2C: return esz() * (size_t)std::max<long long>(ex, (long long)tile * n) * 2;
+      case JIT_C2R: return esz() * ((size_t)ex * 2 + (size_t)tile * (n + 1));
+      default: return esz() * (size_t)ex * pingpong;
     }
   }
 };
@@ -219,8 +230,7 @@ int compile(const JitSpec& spec, std::vector<char>* cubin, std::string* lowered,
   const Nvrtc& rtc = nvrtc();
   if (!rtc.ok) return fail(B200FFT_ERR_UNSUPPORTED, "run-time compilation unavailable: %s", rtc.why.c_str());
   const auto t0 = std::chrono::steady_clock::now();
-  std::string src;
-  if (spec.packed) src += "#define B200FFT_PACKED 1\n";
+  std::string src = spec.defines();
   src += "#include \"fast.cuh\"\n";
   src += "extern \"C\" __device__ unsigned long long b200fft_jit_smem_bytes = (unsigned long long)" + spec.smem_expression() + ";\n";
   const char* headers[] = {k_src_rtc_prelude, k_src_dft, k_src_tma, k_src_fast};
@@ -367,7 +377,9 @@ bool jit_group_cap(const std::vector<uint32_t>& ordered, int cap, std::vector<in
 // stages, codelets up to JIT_WIDE_RADIX are tried and kept if they save a stage (1000 = 10 x 10 x 10 -> 40 x 25: one
 // shared-memory exchange instead of two).   B200FFT_JIT_MAX_RADIX=<r> overrides the wide cap (A/B knob).
 constexpr int JIT_WIDE_RADIX = 50;
-bool jit_group(const std::vector<uint32_t>& ordered, std::vector<int>* out) {
+constexpr int JIT_MAX_RADIX_F64 = 16;  // a radix-16 fp64 butterfly already holds 64 registers of data
+bool jit_group(const std::vector<uint32_t>& ordered, std::vector<int>* out, bool f64 = false) {
+  if (f64) return jit_group_cap(ordered, JIT_MAX_RADIX_F64, out);
   if (!jit_group_cap(ordered, JIT_MAX_RADIX, out)) return false;
   int wide = JIT_WIDE_RADIX;
   if (const char* e = getenv("B200FFT_JIT_MAX_RADIX")) wide = std::max(2, std::min(64, atoi(e)));
@@ -402,7 +414,7 @@ bool jit_geometry(JitSpec* s, long long inner) {
     if (smem > 200 * 1024) continue;
     if (s->kind == JIT_R2C_REG && ((long long)tile * (s->n / rlast)) % 32 != 0) continue;  // r2c_reg_ok(): whole warps per row group
     const long long work = tile * per;
-    const double bytes = (double)tile * s->n * 8;
+    const double bytes = (double)tile * s->n * (double)s->esz();
     for (int rounds = 1; rounds <= 4; ++rounds) {
       long long nt = ((work + rounds - 1) / rounds + 31) / 32 * 32;
       if (nt < 64 && rounds > 1) continue;
@@ -437,9 +449,9 @@ struct JitPass : Pass {
   AxisView view;
   int device = 0;
   bool do_scale = false;
-  float scale = 1.f;
-  float2* d_tw = nullptr;
-  float2* d_tw2 = nullptr;  // W_n^{+-k} of the Hermitian unpack / pack
+  double scale = 1.0;
+  void* d_tw = nullptr;   // stage twiddles, float2 or double2
+  void* d_tw2 = nullptr;  // W_n^{+-k} of the Hermitian unpack / pack
   size_t smem = 0;
   std::string text;
 
@@ -461,47 +473,65 @@ struct JitPass : Pass {
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return B200FFT_OK;
   }
-  ColsArgs cols_args(const void* src, void* dst) const {
-    ColsArgs ca;
+  // Kernel argument blocks. The fp64 build of a kernel sees the same structs with float -> double (rtc_prelude.cuh), so
+  // the host fills a struct of that layout.
+  struct RowsArgs64 { const void* in; double2* out; const double2* tw; long long nrows; double scale; int do_scale; };
+  struct ColsArgs64 { const void* in; double2* out; const double2* tw; long long inner; int tiles_per_outer; double scale; int do_scale; };
+  struct HalfArgs64 { const void* in; void* out; const double2* tw; const double2* tw2; long long nrows; double scale; };
+  template <class A, class T2>
+  A cols_args(const void* src, void* dst) const {
+    A ca;
     ca.in = src;
-    ca.out = reinterpret_cast<float2*>(dst);
-    ca.tw = d_tw;
+    ca.out = reinterpret_cast<T2*>(dst);
+    ca.tw = reinterpret_cast<const T2*>(d_tw);
     ca.inner = view.inner;
     ca.tiles_per_outer = (int)((view.inner + spec.tile - 1) / spec.tile);
     ca.scale = scale;
     ca.do_scale = do_scale;
     return ca;
   }
+  template <class A, class T2>
+  int launch_rows(const void* src, void* dst, int64_t outer, cudaStream_t stream) {
+    A ra;
+    ra.in = src;
+    ra.out = reinterpret_cast<T2*>(dst);
+    ra.tw = reinterpret_cast<const T2*>(d_tw);
+    ra.nrows = outer;
+    ra.scale = scale;
+    ra.do_scale = do_scale;
+    void* params[1] = {&ra};
+    return run(*k, spec, (outer + spec.tile - 1) / spec.tile, params, stream);
+  }
+  template <class A, class T2>
+  int launch_half(const void* src, void* dst, int64_t outer, cudaStream_t stream) {
+    A ha;
+    ha.in = src;
+    ha.out = dst;
+    ha.tw = reinterpret_cast<const T2*>(d_tw);
+    ha.tw2 = reinterpret_cast<const T2*>(d_tw2);
+    ha.nrows = outer;
+    ha.scale = scale;
+    void* params[1] = {&ha};
+    return run(*k, spec, (outer + spec.tile - 1) / spec.tile, params, stream);
+  }
   int launch_outer(const void* src, void* dst, int64_t outer, cudaStream_t stream) {
-    void* params[1];
-    if (spec.kind == JIT_ROWS) {
-      RowsArgs ra;
-      ra.in = src;
-      ra.out = reinterpret_cast<float2*>(dst);
-      ra.tw = d_tw;
-      ra.nrows = outer;
-      ra.scale = scale;
-      ra.do_scale = do_scale;
-      params[0] = &ra;
-      return run(*k, spec, (outer + spec.tile - 1) / spec.tile, params, stream);
-    }
+    if (spec.kind == JIT_ROWS)
+      return spec.f64 ? launch_rows<RowsArgs64, double2>(src, dst, outer, stream) : launch_rows<RowsArgs, float2>(src, dst, outer, stream);
     if (spec.kind == JIT_COLS) {
-      ColsArgs ca = cols_args(src, dst);
+      void* params[1];
+      if (spec.f64) {
+        ColsArgs64 ca = cols_args<ColsArgs64, double2>(src, dst);
+        params[0] = &ca;
+        return run(*k, spec, outer * ca.tiles_per_outer, params, stream);
+      }
+      ColsArgs ca = cols_args<ColsArgs, float2>(src, dst);
       params[0] = &ca;
       return run(*k, spec, outer * ca.tiles_per_outer, params, stream);
     }
-    HalfArgs ha;  // the half-spectrum row kernels
-    ha.in = src;
-    ha.out = dst;
-    ha.tw = d_tw;
-    ha.tw2 = d_tw2;
-    ha.nrows = outer;
-    ha.scale = scale;
-    params[0] = &ha;
-    return run(*k, spec, (outer + spec.tile - 1) / spec.tile, params, stream);
+    return spec.f64 ? launch_half<HalfArgs64, double2>(src, dst, outer, stream) : launch_half<HalfArgs, float2>(src, dst, outer, stream);
   }
   int launch_scatter(const void* src, const Scatter& sc, int64_t nbatch, cudaStream_t stream) override {
-    if (spec.kind != JIT_COLS || spec.real_in) return fail(B200FFT_ERR_UNSUPPORTED, "no scattering store for %s", text.c_str());
+    if (spec.kind != JIT_COLS || spec.real_in || spec.in_dtype != (spec.f64 ? B200FFT_F64 : B200FFT_F32)) return fail(B200FFT_ERR_UNSUPPORTED, "no scattering store for %s", text.c_str());
     if (sc.npeers < 1 || sc.npeers > 16 || view.n % sc.npeers)
       return fail(B200FFT_ERR_INVALID_ARG, "split axis length %lld is not divisible by %d peers", (long long)view.n, sc.npeers);
     JitSpec sp = spec;
@@ -514,17 +544,50 @@ struct JitPass : Pass {
       if (cur != device && cur >= 0) cudaSetDevice(cur);
       if (!k_scatter) return fail(B200FFT_ERR_UNSUPPORTED, "could not specialise the scattering store for %s", text.c_str());
     }
-    ColsArgs ca = cols_args(src, nullptr);
-    ScatterArgs sa;
+    ScatterArgs sa;  // pointers and integers only: the same block for both precisions
     for (int i = 0; i < 16; ++i) sa.peer[i] = i < sc.npeers ? reinterpret_cast<float2*>(sc.peer_out[i]) : nullptr;
     sa.yl = (int)(view.n / sc.npeers);
     const long long outer = nbatch * view.outer_per_batch;
     sa.zbase = (long long)sc.my_rank * outer;
+    if (spec.f64) {
+      ColsArgs64 ca = cols_args<ColsArgs64, double2>(src, nullptr);
+      void* params[2] = {&ca, &sa};
+      return run(*k_scatter, sp, outer * ca.tiles_per_outer, params, stream);
+    }
+    ColsArgs ca = cols_args<ColsArgs, float2>(src, nullptr);
     void* params[2] = {&ca, &sa};
     return run(*k_scatter, sp, outer * ca.tiles_per_outer, params, stream);
   }
   std::string describe() const override { return text; }
 };
+
+// fp64 forms of build_twiddles / build_half_twiddles (fast_registry.cu): tw[(j-1)*P + p] = W_{P*R}^{j*p} per stage s >= 1
+std::vector<double2> stage_twiddles64(const std::vector<int>& radices, bool inverse) {
+  std::vector<double2> t;
+  long long P = 1;
+  for (size_t s = 0; s < radices.size(); ++s) {
+    const int R = radices[s];
+    if (s > 0) {
+      const long long Q = P * R;
+      for (int j = 1; j < R; ++j)
+        for (long long p = 0; p < P; ++p) {
+          const long double th = 2.0L * 3.14159265358979323846264338327950288L * (long double)((j * p) % Q) / (long double)Q;
+          t.push_back(make_double2((double)cosl(th), (double)((inverse ? 1.0L : -1.0L) * sinl(th))));
+        }
+    }
+    P *= R;
+  }
+  if (t.empty()) t.push_back(make_double2(1.0, 0.0));
+  return t;
+}
+std::vector<double2> half_twiddles64(long long n, bool inverse) {
+  std::vector<double2> t;
+  for (long long k = 0; k <= n / 2; ++k) {
+    const long double th = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+    t.push_back(make_double2((double)cosl(th), (double)((inverse ? 1.0L : -1.0L) * sinl(th))));
+  }
+  return t;
+}
 
 bool jit_enabled() {
   const char* e = getenv("B200FFT_JIT");
@@ -532,26 +595,31 @@ bool jit_enabled() {
 }
 
 // kind + transform length + stage list for one axis; false when this tier does not serve it
-bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, bool inverse, HalfMode half, JitSpec* spec) {
+bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, bool inverse, HalfMode half, bool f64,
+                   JitSpec* spec) {
   spec->inverse = inverse;
   spec->real_in = src.comps == 1;
+  spec->f64 = f64;
+  spec->in_dtype = src.dtype;
+  if (half == HALF_C2R && src.dtype != (f64 ? B200FFT_F64 : B200FFT_F32)) return false;  // the staged half spectrum is read as is
+  if (half != HALF_NONE && src.dtype == B200FFT_U8) return false;
   if (half == HALF_NONE) {
     spec->kind = view.inner != 1 ? JIT_COLS : JIT_ROWS;
     spec->n = (int)view.n;
-    if (!jit_group(ax.ordered, &spec->radices)) return false;
+    if (!jit_group(ax.ordered, &spec->radices, f64)) return false;
   } else {
     if (view.inner != 1) return false;  // half-spectrum handling is a row pass
     if (view.n % 2) {
       if (half != HALF_R2C) return false;  // C2R of odd lengths stays on the runtime-length tier
       spec->kind = JIT_R2C_ODD;
       spec->n = (int)view.n;
-      if (!jit_group(ax.ordered, &spec->radices)) return false;
+      if (!jit_group(ax.ordered, &spec->radices, f64)) return false;
     } else {
       // n = 2H real points as an H-point complex transform: the user's stage list with one factor 2 removed
       spec->n = (int)(view.n / 2);
       bool ok = false;
       for (const auto& o : drop_factor_two(ax.ordered))
-        if (jit_group(o, &spec->radices)) { ok = true; break; }
+        if (jit_group(o, &spec->radices, f64)) { ok = true; break; }
       if (!ok) return false;
       if (spec->n == 1) return false;
       spec->kind = half == HALF_C2R ? JIT_C2R : JIT_R2C;
@@ -562,7 +630,7 @@ bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, 
   }
   // packed FADD2 adds: the measured win for mixed-radix and strided kernels, a loss for contiguous power-of-two rows
   // (dft.cuh, profiles/r1_packed_fadd2.md)
-  spec->packed = spec->strided() || (spec->n & (spec->n - 1)) != 0;
+  spec->packed = !f64 && (spec->strided() || (spec->n & (spec->n - 1)) != 0);
   if (!jit_geometry(spec, view.inner)) {
     if (spec->kind != JIT_R2C_REG) return false;
     spec->kind = JIT_R2C;  // no tile keeps whole warps per row group: the shared-memory unpack
@@ -577,9 +645,10 @@ std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView
                                     HalfMode half) {
   const Problem& p = plan.prob;
   if (!jit_enabled()) return nullptr;
-  if (p.desc.out_dtype != B200FFT_F32 || src.dtype != B200FFT_F32 || view.n > 16384 || view.n < 2) return nullptr;
+  if (view.n > 16384 || view.n < 2) return nullptr;
+  const bool f64 = p.desc.out_dtype == B200FFT_F64;
   JitSpec spec;
-  if (!jit_plan_axis(p.axes[axis], view, src, p.desc.inverse != 0, half, &spec)) return nullptr;
+  if (!jit_plan_axis(p.axes[axis], view, src, p.desc.inverse != 0, half, f64, &spec)) return nullptr;
   std::shared_ptr<JitKernel> k = get_kernel(spec, plan.device);
   if (!k) return nullptr;
   auto pass = std::make_unique<JitPass>();
@@ -588,17 +657,29 @@ std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView
   pass->view = view;
   pass->device = plan.device;
   pass->do_scale = scale_inverse;
-  pass->scale = scale_inverse ? (float)(1.0 / (double)view.n) : 1.f;
-  if (half == HALF_C2R) pass->scale = (float)(1.0 / (double)view.n);  // the half-spectrum inverse is always normalised
+  pass->scale = (scale_inverse || half == HALF_C2R) ? 1.0 / (double)view.n : 1.0;  // the half-spectrum inverse is always normalised
   pass->smem = spec.smem();
-  auto upload = [&](const std::vector<float2>& t, float2** d) {
-    if (cudaMalloc(d, t.size() * sizeof(float2)) != cudaSuccess) { cudaGetLastError(); return false; }
+  auto upload = [&](const void* data, size_t bytes, void** d) {
+    if (cudaMalloc(d, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
     plan.owned_device.push_back(*d);  // owned by the plan before the copy: a failed copy must not leak it
-    return cudaMemcpy(*d, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+    return cudaMemcpy(*d, data, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
-  if (!upload(build_twiddles(spec.radices, spec.inverse), &pass->d_tw)) return nullptr;
-  if (half != HALF_NONE && spec.kind != JIT_R2C_ODD && !upload(build_half_twiddles(view.n, half == HALF_C2R), &pass->d_tw2))
-    return nullptr;
+  const bool need_tw2 = half != HALF_NONE && spec.kind != JIT_R2C_ODD;
+  if (f64) {
+    const std::vector<double2> tw = stage_twiddles64(spec.radices, spec.inverse);
+    if (!upload(tw.data(), tw.size() * sizeof(double2), &pass->d_tw)) return nullptr;
+    if (need_tw2) {
+      const std::vector<double2> t2 = half_twiddles64(view.n, half == HALF_C2R);
+      if (!upload(t2.data(), t2.size() * sizeof(double2), &pass->d_tw2)) return nullptr;
+    }
+  } else {
+    const std::vector<float2> tw = build_twiddles(spec.radices, spec.inverse);
+    if (!upload(tw.data(), tw.size() * sizeof(float2), &pass->d_tw)) return nullptr;
+    if (need_tw2) {
+      const std::vector<float2> t2 = build_half_twiddles(view.n, half == HALF_C2R);
+      if (!upload(t2.data(), t2.size() * sizeof(float2), &pass->d_tw2)) return nullptr;
+    }
+  }
   std::string stages;
   for (uint32_t r : p.axes[axis].ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
   char buf[400];
@@ -615,7 +696,7 @@ std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView
 // Host-only probe (no CUDA device needed): compile the kernel the planner would pick for one axis and report it.
 // half: 0 = complex / real-input full spectrum, 1 = R2C rows, 2 = C2R rows
 int jit_probe(int64_t n, int64_t inner, const std::vector<uint32_t>& ordered, bool inverse, bool real_in, int half,
-              std::string* report) {
+              int in_dtype, int out_dtype, std::string* report) {
   AxisSpec ax;
   ax.n = n;
   ax.ordered = ordered;
@@ -624,8 +705,9 @@ int jit_probe(int64_t n, int64_t inner, const std::vector<uint32_t>& ordered, bo
   view.inner = inner;
   IoSpec src;
   src.comps = real_in ? 1 : 2;
+  src.dtype = in_dtype;
   JitSpec spec;
-  if (!jit_plan_axis(ax, view, src, inverse, (HalfMode)half, &spec))
+  if (!jit_plan_axis(ax, view, src, inverse, (HalfMode)half, out_dtype == B200FFT_F64, &spec))
     return fail(B200FFT_ERR_UNSUPPORTED, "the specialisation tier does not serve this axis (radix above %d, or no tile fits)", JIT_MAX_PRIME);
   std::vector<char> cubin;
   std::string lowered, log;

@@ -117,7 +117,7 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan);
 std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src, bool scale_inverse,
                                     HalfMode half);
 int jit_probe(int64_t n, int64_t inner, const std::vector<uint32_t>& ordered, bool inverse, bool real_in, int half,
-              std::string* report);
+              int in_dtype, int out_dtype, std::string* report);
 // number of registered kernel variants per tier (host-only; triggers the one-time registration)
 size_t fast_variant_count();
 size_t fused_variant_count();

@@ -115,7 +115,7 @@ SYMBOLS = [
     ("b200fft_default_bases", ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, _u32p, ctypes.c_int]),
     ("b200fft_plan_dry_run", ctypes.c_int, [ctypes.POINTER(_Desc), ctypes.c_char_p, ctypes.c_size_t]),
     ("b200fft_jit_probe", ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, _u32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                          ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
     ("b200fft_schedule_dry_run", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int64,
                                                  ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     ("b200fft_strerror", ctypes.c_char_p, [ctypes.c_int]),
@@ -230,12 +230,12 @@ def schedule(phases, batch):
     return [tuple(int(out[4 * i + k]) for k in range(4)) for i in range(n)]
 
 
-def jit_probe(n, inner=1, bases=None, inverse=False, real_in=False, half=0):
+def jit_probe(n, inner=1, bases=None, inverse=False, real_in=False, half=0, in_dtype="float32", out_dtype="float32"):
     """Compile (NVRTC, no GPU needed) the specialised kernel the planner would pick for one axis; returns its report."""
     arr = (ctypes.c_uint32 * len(bases))(*bases) if bases else None
     buf = ctypes.create_string_buffer(1024)
     _check(lib().b200fft_jit_probe(n, inner, arr, len(bases) if bases else 0, 1 if inverse else 0, 1 if real_in else 0, half,
-                                   buf, len(buf)))
+                                   _dtype_code(in_dtype), _dtype_code(out_dtype), buf, len(buf)))
     return buf.value.decode()
 
 

@@ -243,7 +243,8 @@ B200FFT_API int b200fft_plan_dry_run(const b200fft_desc* desc, char* buf, size_t
  * planner would pick for ONE axis (length n, element stride `inner`, user bases or NULL for the default rule) and
  * writes "<variant>: <template-id>, smem, cubin size, compile time, symbol" into buf. Needs libnvrtc but no GPU. */
 B200FFT_API int b200fft_jit_probe(int64_t n, int64_t inner, const uint32_t* bases, int nbases, int inverse, int real_in,
-                                  int half /* 0 complex, 1 half-spectrum R2C rows, 2 C2R rows */, char* buf, size_t cap);
+                                  int half /* 0 complex, 1 half-spectrum R2C rows, 2 C2R rows */, int in_dtype, int out_dtype,
+                                  char* buf, size_t cap);
 
 /* Tile schedule of the fused N-d kernel (host logic, no CUDA): phases[p] = {tiles_per_transform,
  * tiles_per_group, dep_div, quota}; writes up to `cap` segments as {phase, first_item, first_tile, count}

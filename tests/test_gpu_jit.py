@@ -169,3 +169,98 @@ def test_jit_scattering_store_in_the_slab_decomposition(monkeypatch):
     want = np.fft.fftn(c2(x))
     assert np.linalg.norm(c2(h_out) - want) <= 2e-6 * np.sqrt(3) * np.linalg.norm(want)
     plan.destroy()
+
+
+F64_CASES = [
+    # shape, in dtype, comps, inverse, bases
+    ((20, 1024), "float64", 2, False, None),
+    ((20, 1024), "float64", 2, True, None),
+    ((6, 64, 64, 64), "float64", 2, False, None),           # registered fp32 lengths: fp64 goes through NVRTC too
+    ((9, 93), "float64", 2, False, [[31, 3]]),
+    ((4, 640, 480), "float64", 2, True, None),
+    ((5, 100), "uint8", 1, False, None),                     # the reference's tests: uint8 in, float64 out (tests.mojo:394)
+    ((3, 6, 4, 8), "uint8", 1, False, None),
+    ((7, 1000), "float32", 2, False, None),                  # fp32 in, fp64 out
+    ((3, 74), "float64", 2, False, None),                    # 37 x 2
+    ((2, 30, 21), "float64", 1, True, None),
+]
+
+
+@pytest.mark.parametrize("shape,in_dtype,comps,inverse,bases", F64_CASES)
+def test_jit_fp64_output(oracle, shape, in_dtype, comps, inverse, bases):
+    """fp64 output no longer lands on the generic kernel: every axis runs the fp64 build of the compile-time kernels.
+    Tolerance: relative L2 <= 1e-13 x sqrt(axes) against numpy float64 (fp64 round-off of a log-depth transform)."""
+    import torch
+    rng = np.random.default_rng(37)
+    full = shape + (comps,)
+    x = rng.integers(0, 256, size=full).astype(np.uint8) if in_dtype == "uint8" else rng.standard_normal(full).astype(in_dtype)
+    plan = b200fft.plan_fft(in_dtype, "float64", full, shape + (2,), bases=bases, inverse=inverse)
+    desc = plan.describe()
+    assert "_f64" in desc and "generic" not in desc and "rt_" not in desc, desc
+    out = torch.full(shape + (2,), float("nan"), device="cuda", dtype=torch.float64)
+    b200fft.fft(out, torch.from_numpy(x).cuda(), plan=plan)
+    torch.cuda.synchronize()
+    got = c2(out.cpu().numpy())
+    xd = x.astype(np.float64)
+    xc = xd[..., 0] if comps == 1 else c2(xd)
+    axes = tuple(range(1, len(shape)))
+    want = np.fft.ifftn(xc, axes=axes) if inverse else np.fft.fftn(xc, axes=axes)
+    assert np.isfinite(got).all()
+    assert np.linalg.norm(got - want) <= 1e-13 * np.sqrt(len(axes)) * np.linalg.norm(want), desc
+    ref = c2(oracle.ref_fft(x, bases=bases, inverse=inverse, out_dtype=np.float64))
+    assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(want)
+    plan.destroy()
+
+
+@pytest.mark.parametrize("shape,inverse", [((12, 1000), False), ((12, 1000), True), ((3, 40, 128), False), ((3, 40, 128), True),
+                                           ((8, 243), False)])
+def test_jit_fp64_half_spectrum(shape, inverse):
+    import torch
+    rng = np.random.default_rng(41)
+    axes = tuple(range(1, len(shape)))
+    cshape = shape[:-1] + (shape[-1] // 2 + 1,)
+    real = rng.standard_normal(shape)
+    if not inverse:
+        plan = b200fft.plan_fft("float64", "float64", shape + (1,), cshape + (2,), real_mode=b200fft.REAL_HALF)
+        desc = plan.describe()
+        assert "jitr2c" in desc and "_f64" in desc and "generic" not in desc, desc
+        out = torch.full(cshape + (2,), float("nan"), device="cuda", dtype=torch.float64)
+        b200fft.fft(out, torch.from_numpy(real).cuda().unsqueeze(-1), plan=plan)
+        torch.cuda.synchronize()
+        got = c2(out.cpu().numpy())
+        want = np.fft.rfftn(real, axes=axes)
+    else:
+        spec = np.fft.rfftn(real, axes=axes)
+        x = np.stack([spec.real, spec.imag], axis=-1)
+        plan = b200fft.plan_fft("float64", "float64", cshape + (2,), shape + (1,), real_mode=b200fft.REAL_HALF, inverse=True)
+        desc = plan.describe()
+        assert "jitc2r" in desc and "_f64" in desc and "generic" not in desc, desc
+        out = torch.full(shape + (1,), float("nan"), device="cuda", dtype=torch.float64)
+        b200fft.fft(out, torch.from_numpy(x).cuda(), plan=plan)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()[..., 0]
+        want = real
+    assert np.isfinite(got).all()
+    assert np.linalg.norm(got - want) <= 1e-13 * np.sqrt(len(axes)) * np.linalg.norm(want), desc
+    plan.destroy()
+
+
+def test_jit_fp32_output_from_other_input_types(oracle):
+    """uint8 / fp64 arrays into an fp32 transform: the specialised kernels cast on load (in_scalar, rtc_prelude.cuh)."""
+    import torch
+    rng = np.random.default_rng(43)
+    for shape, in_dtype, comps in (((5, 600), "uint8", 1), ((3, 50, 36), "uint8", 2), ((4, 225), "float64", 2)):
+        full = shape + (comps,)
+        x = rng.integers(0, 256, size=full).astype(np.uint8) if in_dtype == "uint8" else rng.standard_normal(full)
+        plan = b200fft.plan_fft(in_dtype, "float32", full, shape + (2,))
+        desc = plan.describe()
+        assert "jit" in desc and ("_inu8" in desc or "_inf64" in desc) and "generic" not in desc, desc
+        out = torch.full(shape + (2,), float("nan"), device="cuda")
+        b200fft.fft(out, torch.from_numpy(x).cuda(), plan=plan)
+        torch.cuda.synchronize()
+        xd = x.astype(np.float64)
+        xc = xd[..., 0] if comps == 1 else c2(xd)
+        want = np.fft.fftn(xc, axes=tuple(range(1, len(shape))))
+        got = c2(out.cpu().numpy())
+        assert np.linalg.norm(got - want) <= 2e-6 * np.sqrt(len(shape) - 1) * np.linalg.norm(want), desc
+        plan.destroy()
