@@ -130,7 +130,11 @@ enum JitKind {
   JIT_R2C,          // rows_r2c_kernel<H, RL, C, NT>: n = 2H real points as an H-point complex row + shared-memory unpack
   JIT_R2C_REG,      // rows_r2c_reg_kernel<H, RL, C, NT>: Hermitian unpack in registers (warp shuffles)
   JIT_R2C_ODD,      // rows_r2c_odd_kernel<N, RL, C, NT>: odd n, the n-point row kernel on real rows, bins 0..n/2 stored
-  JIT_C2R           // rows_c2r_kernel<H, RL, C, NT>: Hermitian pack fused into stage 0 of the H-point inverse
+  JIT_C2R,          // rows_c2r_kernel<H, RL, C, NT>: Hermitian pack fused into stage 0 of the H-point inverse
+  // long axes as two passes, N = N1 * N2 (fast.cuh, "four-step"):
+  JIT_SPLIT_A,      // cols_split_a_kernel<N1, RL, CW, NT, INV>: N1-point strided transforms, W_N^{k1 n2} fused into the store
+  JIT_SPLIT_B_COLS, // cols_split_b_kernel<N2, RL, CW, NT, INV>: N2-point strided transforms, natural-order store
+  JIT_SPLIT_B_ROWS  // rows_split_b_kernel<N2, RL, C, NT, INV>: the same for a contiguous axis
 };
 
 struct JitSpec {
@@ -143,7 +147,8 @@ struct JitSpec {
   int in_dtype = B200FFT_F32;  // element type of the array the kernel READS (cast on load)
 
   size_t esz() const { return f64 ? sizeof(double2) : sizeof(float2); }
-  bool strided() const { return kind == JIT_COLS || kind == JIT_SCATTER; }
+  int tile_divides = 0;        // geometry only: the tile must divide this (split pass B rows never straddle transforms)
+  bool strided() const { return kind == JIT_COLS || kind == JIT_SCATTER || kind == JIT_SPLIT_A || kind == JIT_SPLIT_B_COLS; }
   std::string radix_list() const {
     std::string s;
     for (int r : radices) s += (s.empty() ? "" : ", ") + std::to_string(r);
@@ -163,14 +168,20 @@ struct JitSpec {
       case JIT_R2C: return "b200fft::rows_r2c_kernel<" + head + ">";
       case JIT_R2C_REG: return "b200fft::rows_r2c_reg_kernel<" + head + ">";
       case JIT_R2C_ODD: return "b200fft::rows_r2c_odd_kernel<" + head + ">";
+      case JIT_SPLIT_A: return "b200fft::cols_split_a_kernel<" + head + ", " + inv + ">";
+      case JIT_SPLIT_B_COLS: return "b200fft::cols_split_b_kernel<" + head + ", " + inv + ">";
+      case JIT_SPLIT_B_ROWS: return "b200fft::rows_split_b_kernel<" + head + ", " + inv + ">";
       default: return "b200fft::rows_c2r_kernel<" + head + ">";
     }
   }
   std::string smem_expression() const {  // fast.cuh's own constexpr for the instantiation's dynamic shared memory
     switch (kind) {
       case JIT_ROWS:
+      case JIT_SPLIT_B_ROWS:
       case JIT_R2C_ODD: return "b200fft::rows_smem_bytes<" + shape_args() + ">()";
       case JIT_COLS:
+      case JIT_SPLIT_A:
+      case JIT_SPLIT_B_COLS:
       case JIT_SCATTER: return "b200fft::cols_smem_bytes<" + shape_args() + ">()";
       case JIT_R2C: return "b200fft::rows_r2c_smem_bytes<" + shape_args() + ">()";
       case JIT_R2C_REG: return "b200fft::rows_r2c_reg_smem_bytes<" + shape_args() + ">()";
@@ -178,7 +189,8 @@ struct JitSpec {
     }
   }
   std::string name() const {
-    static const char* const tag[] = {"jitrows", "jitcols", "jitscatter", "jitr2c", "jitr2creg", "jitr2codd", "jitc2r"};
+    static const char* const tag[] = {"jitrows", "jitcols", "jitscatter", "jitr2c", "jitr2creg", "jitr2codd", "jitc2r",
+                                      "jitsplitA", "jitsplitBcols", "jitsplitBrows"};
     return std::string(tag[kind]) + std::to_string(n) + "_" + radix_name(radices) + (strided() ? "_w" : "_c") + std::to_string(tile) +
            "_t" + std::to_string(threads) + (f64 ? "_f64" : "") + (in_dtype == B200FFT_U8 ? "_inu8" : in_dtype == (f64 ? B200FFT_F32 : B200FFT_F64) ? (f64 ? "_inf32" : "_inf64") : "");
   }
@@ -342,7 +354,7 @@ constexpr int JIT_MAX_RADIX = 32;
 constexpr int JIT_MAX_PRIME = 64;
 constexpr int JIT_MAX_STAGES = 5;
 
-bool jit_group_cap(const std::vector<uint32_t>& ordered, int cap, std::vector<int>* out) {
+bool jit_group_cap(const std::vector<uint32_t>& ordered, int cap, std::vector<int>* out, int max_stages = JIT_MAX_STAGES) {
   std::vector<uint32_t> small;
   std::vector<int> big;
   for (uint32_t r : ordered) {
@@ -351,7 +363,7 @@ bool jit_group_cap(const std::vector<uint32_t>& ordered, int cap, std::vector<in
     else small.push_back(r);
   }
   std::sort(small.begin(), small.end(), [](uint32_t x, uint32_t y) { return x > y; });
-  for (int want = small.empty() ? 0 : 1; want + (int)big.size() <= JIT_MAX_STAGES; ++want) {
+  for (int want = small.empty() ? 0 : 1; want + (int)big.size() <= max_stages; ++want) {
     std::vector<long long> g((size_t)want, 1);
     bool ok = true;
     for (uint32_t b : small) {
@@ -413,6 +425,7 @@ bool jit_geometry(JitSpec* s, long long inner) {
     const size_t smem = s->smem();
     if (smem > 200 * 1024) continue;
     if (s->kind == JIT_R2C_REG && ((long long)tile * (s->n / rlast)) % 32 != 0) continue;  // r2c_reg_ok(): whole warps per row group
+    if (s->tile_divides > 0 && s->tile_divides % tile != 0) continue;
     const long long work = tile * per;
     const double bytes = (double)tile * s->n * (double)s->esz();
     for (int rounds = 1; rounds <= 4; ++rounds) {
@@ -639,16 +652,177 @@ bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, 
   return true;
 }
 
+// ---- long axes: N = N1 * N2 as two specialised passes and one plan-owned temporary (split_registry.cu does this for a
+// fixed list of (N1, N2); here any factorisation the stage list allows) ---------------------------------------------------
+struct JitSplitPass : Pass {
+  JitSpec sa, sb;
+  std::shared_ptr<JitKernel> ka, kb;
+  AxisView view;
+  int n1 = 0, n2 = 0;
+  bool do_scale = false;
+  double scale = 1.0;
+  void *twa = nullptr, *twb = nullptr, *tmp = nullptr;
+  const void* twN = nullptr;
+  std::string text;
+
+  struct SplitArgs64 {
+    const double2* in; double2* out; const double2* tw; const double2* twN; long long inner; long long nrows;
+    int tiles_per_outer; int n1, n2; double scale; int do_scale;
+  };
+  template <class A, class T2>
+  int go(const void* src, void* dst, long long outer, cudaStream_t stream) {
+    A a;
+    memset(&a, 0, sizeof a);
+    a.inner = view.inner;
+    a.n1 = n1;
+    a.n2 = n2;
+    a.in = reinterpret_cast<const T2*>(src);  // pass A: view (outer, n1, n2 * inner)
+    a.out = reinterpret_cast<T2*>(tmp);
+    a.tw = reinterpret_cast<const T2*>(twa);
+    a.twN = reinterpret_cast<const T2*>(twN);
+    const long long vinner = (long long)n2 * view.inner;
+    a.tiles_per_outer = (int)((vinner + sa.tile - 1) / sa.tile);
+    void* params[1] = {&a};
+    int rc = launch_one(*ka, sa, outer * a.tiles_per_outer, params, stream);
+    if (rc != B200FFT_OK) return rc;
+    a.in = reinterpret_cast<const T2*>(tmp);  // pass B
+    a.out = reinterpret_cast<T2*>(dst);
+    a.tw = reinterpret_cast<const T2*>(twb);
+    a.scale = scale;
+    a.do_scale = do_scale;
+    long long grid;
+    if (sb.kind == JIT_SPLIT_B_ROWS) {
+      a.nrows = outer * n1;
+      grid = (a.nrows + sb.tile - 1) / sb.tile;
+    } else {
+      a.tiles_per_outer = (int)((view.inner + sb.tile - 1) / sb.tile);
+      grid = outer * n1 * a.tiles_per_outer;
+    }
+    return launch_one(*kb, sb, grid, params, stream);
+  }
+  int launch_one(const JitKernel& kern, const JitSpec& sp, long long grid, void** params, cudaStream_t stream) {
+    if (grid <= 0) return B200FFT_OK;
+    if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many tiles");
+    const CUresult r = driver().LaunchKernel(kern.fn, (unsigned)grid, 1, 1, (unsigned)sp.threads, 1, 1, (unsigned)sp.smem(),
+                                             (CUstream)stream, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(B200FFT_ERR_CUDA, "launch of %s failed (CUresult %d)", sp.name().c_str(), (int)r);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return B200FFT_OK;
+  }
+  int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) override {
+    const long long outer = nbatch * view.outer_per_batch;
+    if (outer <= 0) return B200FFT_OK;
+    return sa.f64 ? go<SplitArgs64, double2>(src, dst, outer, stream) : go<SplitArgs, float2>(src, dst, outer, stream);
+  }
+  std::string describe() const override { return text; }
+  int launches() const override { return 2; }
+};
+
+// Split the grouped super-stage list into the stages of pass A (product N1) and pass B (product N2): both as close to
+// sqrt(N) as the radices allow, each short enough for one tile.
+bool jit_split_stages(const std::vector<int>& radices, std::vector<int>* a, std::vector<int>* b) {
+  const size_t m = radices.size();
+  if (m < 2 || m > 12) return false;
+  double best = 1e300;
+  for (unsigned mask = 1; mask + 1 < (1u << m); ++mask) {
+    long long p1 = 1, p2 = 1;
+    int c1 = 0, c2 = 0;
+    for (size_t i = 0; i < m; ++i) {
+      if (mask >> i & 1) { p1 *= radices[i]; ++c1; }
+      else { p2 *= radices[i]; ++c2; }
+    }
+    if (p1 > 8192 || p2 > 8192 || c1 > 4 || c2 > 4) continue;
+    const double score = std::fabs(std::log2((double)p1 / (double)p2)) + 0.25 * (c1 > c2 ? c1 - c2 : c2 - c1);
+    if (score < best) {
+      best = score;
+      a->clear();
+      b->clear();
+      for (size_t i = 0; i < m; ++i) ((mask >> i & 1) ? a : b)->push_back(radices[i]);
+    }
+  }
+  return best < 1e299;
+}
+
+std::unique_ptr<Pass> make_jit_split_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src, bool scale_inverse) {
+  const Problem& p = plan.prob;
+  const bool f64 = p.desc.out_dtype == B200FFT_F64;
+  if (src.comps != 2 || src.dtype != p.desc.out_dtype || view.n > (1 << 24) || !plan.tw[axis].ptr) return nullptr;
+  std::vector<int> all, ra, rb;
+  // more stages than one tile takes: the cap on the stage count does not apply to the union of the two passes
+  if (!jit_group_cap(p.axes[axis].ordered, f64 ? JIT_MAX_RADIX_F64 : JIT_MAX_RADIX, &all, 8)) return nullptr;
+  if (!jit_split_stages(all, &ra, &rb)) return nullptr;
+  auto pass = std::make_unique<JitSplitPass>();
+  long long n1 = 1, n2 = 1;
+  for (int r : ra) n1 *= r;
+  for (int r : rb) n2 *= r;
+  pass->n1 = (int)n1;
+  pass->n2 = (int)n2;
+  pass->view = view;
+  for (JitSpec* s : {&pass->sa, &pass->sb}) {
+    s->inverse = p.desc.inverse != 0;
+    s->f64 = f64;
+    s->in_dtype = src.dtype;
+    s->packed = !f64;
+  }
+  pass->sa.kind = JIT_SPLIT_A;
+  pass->sa.n = (int)n1;
+  pass->sa.radices = ra;
+  pass->sb.kind = view.inner == 1 ? JIT_SPLIT_B_ROWS : JIT_SPLIT_B_COLS;
+  pass->sb.n = (int)n2;
+  pass->sb.radices = rb;
+  if (view.inner == 1) pass->sb.tile_divides = (int)n1;
+  if (!jit_geometry(&pass->sa, n2 * view.inner) || !jit_geometry(&pass->sb, view.inner)) return nullptr;
+  pass->ka = get_kernel(pass->sa, plan.device);
+  pass->kb = pass->ka ? get_kernel(pass->sb, plan.device) : nullptr;
+  if (!pass->ka || !pass->kb) return nullptr;
+  pass->do_scale = scale_inverse;
+  pass->scale = scale_inverse ? 1.0 / (double)view.n : 1.0;
+  pass->twN = plan.tw[axis].ptr;  // W_N^n, n in [0, N), in the working precision (api.cu: upload_twiddles)
+  auto upload = [&](const void* data, size_t bytes, void** d) {
+    if (cudaMalloc(d, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    plan.owned_device.push_back(*d);
+    return cudaMemcpy(*d, data, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  bool ok;
+  if (f64) {
+    const auto ta = stage_twiddles64(ra, pass->sa.inverse), tb = stage_twiddles64(rb, pass->sa.inverse);
+    ok = upload(ta.data(), ta.size() * sizeof(double2), &pass->twa) && upload(tb.data(), tb.size() * sizeof(double2), &pass->twb);
+  } else {
+    const auto ta = build_twiddles(ra, pass->sa.inverse), tb = build_twiddles(rb, pass->sa.inverse);
+    ok = upload(ta.data(), ta.size() * sizeof(float2), &pass->twa) && upload(tb.data(), tb.size() * sizeof(float2), &pass->twb);
+  }
+  if (!ok) return nullptr;
+  const size_t tmp_bytes = (size_t)p.batch * view.outer_per_batch * view.n * view.inner * pass->sa.esz();
+  if (cudaMalloc(&pass->tmp, tmp_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  plan.owned_device.push_back(pass->tmp);
+  plan.workspace_bytes += tmp_bytes;
+  std::string stages;
+  for (uint32_t r : p.axes[axis].ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
+  if (stages.size() > 120) stages = stages.substr(0, 117) + "...";
+  char buf[640];
+  snprintf(buf, sizeof buf, "axis %d: split n=%lld = %lld x %lld inner=%lld: %s (+W_n twiddle) -> %s (natural-order store); temp=%zuB user "
+           "stages=[%s] [NVRTC, %.0f + %.0f ms]", axis, (long long)view.n, n1, n2, (long long)view.inner, pass->sa.name().c_str(),
+           pass->sb.name().c_str(), tmp_bytes, stages.c_str(), pass->ka->compile_ms, pass->kb->compile_ms);
+  pass->text = buf;
+  return pass;
+}
+
 }  // namespace
 
 std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src, bool scale_inverse,
                                     HalfMode half) {
   const Problem& p = plan.prob;
-  if (!jit_enabled()) return nullptr;
-  if (view.n > 16384 || view.n < 2) return nullptr;
+  if (!jit_enabled() || view.n < 2) return nullptr;
   const bool f64 = p.desc.out_dtype == B200FFT_F64;
   JitSpec spec;
-  if (!jit_plan_axis(p.axes[axis], view, src, p.desc.inverse != 0, half, f64, &spec)) return nullptr;
+  if (view.n > 16384 || !jit_plan_axis(p.axes[axis], view, src, p.desc.inverse != 0, half, f64, &spec)) {
+    // too long (or too many stages) for one tile: two passes, if the axis is a plain complex one
+    if (half != HALF_NONE || view.n < 1024) return nullptr;
+    return make_jit_split_pass(plan, axis, view, src, scale_inverse);
+  }
   std::shared_ptr<JitKernel> k = get_kernel(spec, plan.device);
   if (!k) return nullptr;
   auto pass = std::make_unique<JitPass>();

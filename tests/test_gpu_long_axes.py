@@ -61,3 +61,30 @@ def test_split_respects_user_bases():
     assert "split" not in desc.split("\n")[1] and rel < 2e-6, desc
     rel, mx, desc = _run((2, 1920, 64), bases=[[16, 8, 15], [8, 8]])  # groupable into (16,8) x (15)
     assert "split n=1920 = 128 x 15" in desc and rel < 2e-6, desc
+
+
+@pytest.mark.parametrize("shape,inverse", [((3, 20000), False), ((2, 100000), True), ((1, 1 << 18), False), ((1, 1 << 20), False),
+                                           ((2, 20000, 6), False), ((2, 3, 30000), True), ((1, 5 ** 7), False)])
+def test_long_axes_without_a_registered_split(shape, inverse):
+    """Any long axis whose stage list splits into two tile-sized halves: both passes specialised at plan time
+    (csrc/jit.cu, make_jit_split_pass). These lengths used to return B200FFT_ERR_UNSUPPORTED."""
+    rel, mx, desc = _run(shape, inverse)
+    n = max(shape[1:])
+    assert "split n=%d = " % n in desc and "jitsplitA" in desc and "generic" not in desc, desc
+    assert rel < 2.5e-6 and mx < 1e-5, (rel, mx, desc)
+
+
+def test_long_axis_fp64():
+    import torch
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 10000, 2))
+    plan = b200fft.plan_fft("float64", "float64", x.shape, x.shape)
+    desc = plan.describe()
+    assert "split n=10000" in desc and "_f64" in desc, desc
+    out = torch.full(x.shape, float("nan"), device="cuda", dtype=torch.float64)
+    b200fft.fft(out, torch.from_numpy(x).cuda(), plan=plan)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    want = np.fft.fft(x[..., 0] + 1j * x[..., 1], axis=1)
+    assert np.linalg.norm((got[..., 0] + 1j * got[..., 1]) - want) <= 1e-13 * np.linalg.norm(want), desc
+    plan.destroy()
