@@ -114,6 +114,10 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
     pass->src_sel = ssel;
     pass->dst_sel = dsel;
     pass->axis = axis;
+    {  // B200FFT_SERPENTINE=0 switches the alternating tile order off (A/B knob; profiles/r2_serpentine.md)
+      const char* e = getenv("B200FFT_SERPENTINE");
+      pass->reverse_order = !(e && atoi(e) == 0) && (plan->passes.size() % 2 == 1);
+    }
     plan->passes.push_back(std::move(pass));
     return B200FFT_OK;
   };

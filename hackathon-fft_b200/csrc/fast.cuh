@@ -617,6 +617,8 @@ struct ColsArgs {
   int tiles_per_outer;    // ceil(inner / CW)
   float scale;
   int do_scale;
+  int reverse;            // walk the tiles from the last to the first: the pass before this one wrote the array front to
+                          // back, so its END is what the L2 still holds ("serpentine" pass order, api.cu: build_passes)
 };
 
 // strided axis: tile = all N points of CW adjacent columns (CW*8 contiguous bytes per axis step);
@@ -627,8 +629,9 @@ __global__ void __launch_bounds__(NT) cols_kernel(const __grid_constant__ ColsAr
   constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + BUF;
-  const long long o = blockIdx.x / a.tiles_per_outer;
-  const long long c0 = (long long)(blockIdx.x - o * a.tiles_per_outer) * CW;
+  const unsigned bid = a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const long long o = bid / a.tiles_per_outer;
+  const long long c0 = (long long)(bid - o * a.tiles_per_outer) * CW;
   const long long base = o * N * a.inner + c0;
   const int valid_c = (int)min((long long)CW, a.inner - c0);
   const void* in = REAL ? (const void*)(reinterpret_cast<const in_scalar*>(a.in) + base)

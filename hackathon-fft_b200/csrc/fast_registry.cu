@@ -229,6 +229,7 @@ struct FastPass : Pass {
       a.tiles_per_outer = (int)((view.inner + v->tile - 1) / v->tile);
       a.scale = scale;
       a.do_scale = do_scale;
+      a.reverse = reverse_order ? 1 : 0;
       const long long grid = outer * a.tiles_per_outer;
       if (grid <= 0) return B200FFT_OK;
       if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many column tiles");
@@ -251,6 +252,7 @@ struct FastPass : Pass {
     a.tiles_per_outer = (int)((view.inner + v->tile - 1) / v->tile);
     a.scale = scale;
     a.do_scale = do_scale;
+    a.reverse = 0;
     ScatterArgs sa;
     for (int i = 0; i < 16; ++i) sa.peer[i] = i < sc.npeers ? reinterpret_cast<float2*>(sc.peer_out[i]) : nullptr;
     sa.yl = (int)(view.n / sc.npeers);

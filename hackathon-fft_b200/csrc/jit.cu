@@ -489,7 +489,7 @@ struct JitPass : Pass {
   // Kernel argument blocks. The fp64 build of a kernel sees the same structs with float -> double (rtc_prelude.cuh), so
   // the host fills a struct of that layout.
   struct RowsArgs64 { const void* in; double2* out; const double2* tw; long long nrows; double scale; int do_scale; };
-  struct ColsArgs64 { const void* in; double2* out; const double2* tw; long long inner; int tiles_per_outer; double scale; int do_scale; };
+  struct ColsArgs64 { const void* in; double2* out; const double2* tw; long long inner; int tiles_per_outer; double scale; int do_scale; int reverse; };
   struct HalfArgs64 { const void* in; void* out; const double2* tw; const double2* tw2; long long nrows; double scale; };
   template <class A, class T2>
   A cols_args(const void* src, void* dst) const {
@@ -501,6 +501,7 @@ struct JitPass : Pass {
     ca.tiles_per_outer = (int)((view.inner + spec.tile - 1) / spec.tile);
     ca.scale = scale;
     ca.do_scale = do_scale;
+    ca.reverse = (dst != nullptr && reverse_order) ? 1 : 0;  // (dst == nullptr: the scattering store keeps the forward order)
     return ca;
   }
   template <class A, class T2>

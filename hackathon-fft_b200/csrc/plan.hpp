@@ -58,6 +58,9 @@ struct Pass {
   }
   int axis = -1;
   BufSel src_sel = BUF_OUTPUT, dst_sel = BUF_OUTPUT;
+  // Serpentine pass order: every second pass of a per-axis plan walks its tiles back to front, starting on the part
+  // of the array the previous pass wrote last (still in L2) instead of the part it wrote first (long evicted).
+  bool reverse_order = false;
   // A pass that stands for ALL axes (the fused N-d kernel) carries the per-axis passes of the same plan: they run
   // in its place when its launch is refused (cooperative launch cannot be satisfied on this context).
   std::vector<std::unique_ptr<Pass>> fallback;
