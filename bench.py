@@ -60,6 +60,10 @@ SHAPES = [
     ("3d_100x64x64x64_r2c_half", (100, 64, 64, 64), "half"),
     ("3d_10x128x128x128_r2c_half", (10, 128, 128, 128), "half"),
     ("3d_1x256x256x256_r2c_half", (1, 256, 256, 256), "half"),
+    # lengths WITHOUT a hand-registered kernel variant: specialised at plan time through NVRTC (csrc/jit.cu), the
+    # counterpart of the reference specialising every shape at compile time (profiles/r2_jit_tier.md)
+    ("1d_50000x1000_plan_time_specialised", (50000, 1000), False),
+    ("3d_4x200x200x200_plan_time_specialised", (4, 200, 200, 200), False),
 ]
 
 
@@ -331,6 +335,20 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+_TRAFFIC = None
+
+
+def _plan_traffic():
+    global _TRAFFIC
+    if _TRAFFIC is None:
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                _TRAFFIC = json.load(f)
+        except Exception:
+            _TRAFFIC = {}
+    return _TRAFFIC
+
+
 def bench_shape(name, shape, real_in, torch, b200fft, steps, warmup, peak):
     """ours vs cuFFT on one shape, same buffers, same stream, CUDA events."""
     comps = 1 if real_in else 2
@@ -349,6 +367,12 @@ def bench_shape(name, shape, real_in, torch, b200fft, steps, warmup, peak):
         row.update({"ms": ms, "gflops": flops_c2c(shape) * (0.5 if real_in else 1.0) / ms / 1e6,
                     "gbs": ab / ms / 1e6, "hbm_frac": ab / ms / 1e6 / peak, "launches": plan.launches,
                     "kernels": plan.describe().strip().split("\n")})
+        # DRAM bytes of one exec of this plan (all its launches) from a committed ncu capture, over the algorithmic bytes:
+        # > 1 = passes re-reading what did not stay in L2 (profiles/traffic.json, tools/ncu_summary.py "plan:" entries)
+        tr = _plan_traffic().get("plan:" + name)
+        if tr and tr.get("dram_bytes_per_exec"):
+            row["traffic_over_algorithmic"] = tr["dram_bytes_per_exec"] / ab
+            row["traffic_source"] = tr.get("source")
         # parity on one batch item against numpy f64
         ref_in = x[0].double().cpu().numpy()
         want = np.fft.rfftn(ref_in[..., 0]) if half else np.fft.fftn(ref_in[..., 0] + (1j * ref_in[..., 1] if comps == 2 else 0))

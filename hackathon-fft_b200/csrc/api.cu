@@ -377,6 +377,18 @@ int b200fft_plan_create(b200fft_plan** out, const b200fft_desc* desc) {
   plan_pass_group(plan.get());
   for (int i = 0; i < plan->group_passes; ++i)
     if (!plan->passes[(size_t)i]->supports_units()) plan->group_passes = 0;  // a pass kind without unit launches: no grouping
+  if (plan->group_passes >= 2) {
+    const char* e = getenv("B200FFT_PASS_PIPELINE");  // 0 = run the group's chunks serially on the caller's stream
+    plan->group_pipeline = !(e && atoi(e) == 0);
+    if (plan->group_pipeline) {
+      bool ok = cudaStreamCreateWithFlags(&plan->group_stream, cudaStreamNonBlocking) == cudaSuccess;
+      for (auto& ev : plan->group_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) {
+        cudaGetLastError();
+        plan->group_pipeline = false;
+      }
+    }
+  }
   // The tables were uploaded with cudaMemcpy from pageable memory on the legacy stream: make sure they have landed
   // before the caller launches on a non-blocking stream of its own (which is not ordered after the legacy stream).
   if (cudaError_t e = cudaDeviceSynchronize(); e != cudaSuccess) {
@@ -403,6 +415,9 @@ int b200fft_plan_destroy(b200fft_plan* plan) {
     if (plan->hs[i]) cudaStreamDestroy(plan->hs[i]);
   for (auto& e : plan->h_ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : plan->group_ev)
+    if (e) cudaEventDestroy(e);
+  if (plan->group_stream) cudaStreamDestroy(plan->group_stream);
   delete plan;
   return B200FFT_OK;
 }
@@ -416,15 +431,41 @@ static int run_passes(b200fft_plan* plan, void* d_out, const void* d_in, int64_t
     // the L2-resident group (see plan_pass_group): all its passes per chunk of units, input -> output then in place
     first = (size_t)plan->group_passes;
     const int64_t units = nbatch * plan->group_mult;
-    for (int64_t u0 = 0; u0 < units; u0 += plan->group_chunk_units) {
+    auto launch_chunk = [&](size_t i, int64_t u0, cudaStream_t s) -> int {
       const int64_t nu = std::min<int64_t>(plan->group_chunk_units, units - u0);
       char* out_c = (char*)d_out + (size_t)u0 * plan->group_out_stride;
       const char* in_c = (const char*)d_in + (size_t)u0 * plan->group_in_stride;
-      for (size_t i = 0; i < first; ++i) {
-        Pass& pass = *plan->passes[i];
-        int rc = pass.launch_units(pass.src_sel == BUF_INPUT ? (const void*)in_c : (const void*)out_c, out_c, nu, plan->group_mult, st);
+      Pass& pass = *plan->passes[i];
+      return pass.launch_units(pass.src_sel == BUF_INPUT ? (const void*)in_c : (const void*)out_c, out_c, nu, plan->group_mult, s);
+    };
+    if (plan->group_pipeline && plan->group_stream) {
+      // Two streams: pass 0 of chunk k on the caller's stream, passes 1.. of chunk k on the side stream as soon as it is
+      // done, while pass 0 of chunk k+1 already runs: the kernels' ramps and tails overlap, and pass 0 may run at most
+      // two chunks ahead so that what sits between the streams stays L2-resident.
+      cudaStream_t s2 = plan->group_stream;
+      cudaEvent_t ev_fork = plan->group_ev[0], ev_first = plan->group_ev[1];
+      cudaEvent_t* ev_tail = &plan->group_ev[2];
+      B200_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+      B200_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_fork, 0));
+      int64_t k = 0;
+      for (int64_t u0 = 0; u0 < units; u0 += plan->group_chunk_units, ++k) {
+        if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(st, ev_tail[k & 1], 0));
+        int rc = launch_chunk(0, u0, st);
         if (rc != B200FFT_OK) return rc;
+        B200_CUDA_CHECK(cudaEventRecord(ev_first, st));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_first, 0));
+        for (size_t i = 1; i < first; ++i)
+          if ((rc = launch_chunk(i, u0, s2)) != B200FFT_OK) return rc;
+        B200_CUDA_CHECK(cudaEventRecord(ev_tail[k & 1], s2));
       }
+      B200_CUDA_CHECK(cudaStreamWaitEvent(st, ev_tail[(k - 1) & 1], 0));  // join: everything after this sees the group's result
+      if (k >= 2) B200_CUDA_CHECK(cudaStreamWaitEvent(st, ev_tail[k & 1], 0));
+    } else {
+      for (int64_t u0 = 0; u0 < units; u0 += plan->group_chunk_units)
+        for (size_t i = 0; i < first; ++i) {
+          int rc = launch_chunk(i, u0, st);
+          if (rc != B200FFT_OK) return rc;
+        }
     }
   }
   for (size_t i = first; i < plan->passes.size(); ++i) {

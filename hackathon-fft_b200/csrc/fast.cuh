@@ -560,43 +560,71 @@ __global__ void __launch_bounds__(NT) rows_r2c_odd_kernel(const __grid_constant_
   run_axis<RL, N, C, 1, NT, false, RowLayoutN<N>::template type>(src, dst, smem_f2, smem_f2 + BUF, a.tw, 1.f, false);
 }
 
-// stage-0 source of the C2R kernel: Z[k] from the staged half spectrum
+// the same source reading the half spectrum straight from global memory: X[i] and X[H - i] are both in the tile's own
+// rows, so the second read of every element is an L1 / L2 hit, and the kernel needs no staging buffer, no staging
+// barrier and only the exchange buffer(s) of the H-point transform (rows_c2r_kernel used to stage the C x (H + 1) bins
+// in shared memory first: 100 KB per CTA for H = 512, two CTAs per SM, 100000 x 1024 C2R at 0.31 ms; now 3-6 CTAs).
 template <int H>
-struct HermSrc {
-  const float2* xb;  // [rows][H+1]
+struct HermGlobalSrc {
+  const in_vec2* __restrict__ xb;  // [rows][H+1] in global memory
   const float2* __restrict__ tw2;
+  int valid_o;
   __device__ __forceinline__ float2 load(int o, int i, int) const {
-    const float2 xk = xb[o * (H + 1) + i];
-    float2 xm = xb[o * (H + 1) + H - i];
-    xm.y = -xm.y;
+    if (o >= valid_o) return make_float2(0.f, 0.f);
+    const in_vec2 a = __ldg(&xb[(long long)o * (H + 1) + i]);
+    const in_vec2 b = __ldg(&xb[(long long)o * (H + 1) + H - i]);
+    const float2 xk = make_float2((float)a.x, (float)a.y), xm = make_float2((float)b.x, -(float)b.y);
     const float2 s = make_float2(xk.x + xm.x, xk.y + xm.y), d = make_float2(xk.x - xm.x, xk.y - xm.y);
     const float2 t = cmulf(d, __ldg(&tw2[i]));  // W_n^{-i} * (X[i] - conj(X[H-i]))
     return make_float2(s.x - t.y, s.y + t.x);   // s + i t
   }
 };
 
+// (min 3 CTAs per SM for CTAs of up to 256 threads: <512, 32x16, 8, 256> sat at 83 registers = two CTAs)
 template <int H, class RL, int C, int NT>
-__global__ void __launch_bounds__(NT) rows_c2r_kernel(const __grid_constant__ HalfArgs a) {
+__global__ void __launch_bounds__(NT, NT <= 256 ? 3 : 1) rows_c2r_kernel(const __grid_constant__ HalfArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
   constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + EX;
-  float2* xbuf = smem_f2 + 2 * EX;  // [C][H+1]
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
-  const in_vec2* __restrict__ in = reinterpret_cast<const in_vec2*>(a.in) + row0 * (H + 1);
-  for (int idx = threadIdx.x; idx < C * (H + 1); idx += NT) {
-    float2 v = make_float2(0.f, 0.f);
-    if (idx < valid * (H + 1)) {
-      const in_vec2 w = __ldg(&in[idx]);
-      v = make_float2((float)w.x, (float)w.y);
-    }
-    xbuf[idx] = v;
-  }
-  __syncthreads();
+  HermGlobalSrc<H> src{reinterpret_cast<const in_vec2*>(a.in) + row0 * (H + 1), a.tw2, valid};
   GlobalDst dst{reinterpret_cast<float2*>(a.out) + row0 * H, H, 1, valid, 1};
-  run_axis<RL, H, C, 1, NT, true, RowLayoutN<H>::template type>(HermSrc<H>{xbuf, a.tw2}, dst, buf0, buf1, a.tw, a.scale,
-                                                                true);
+  run_axis<RL, H, C, 1, NT, true, RowLayoutN<H>::template type>(src, dst, buf0, buf1, a.tw, a.scale, true);
+}
+
+// C2R of an ODD length n: the n-point inverse on the Hermitian-extended row (X[n - k] = conj X[k], read on the fly from
+// the n/2 + 1 stored bins), real parts stored. Mirror image of rows_r2c_odd_kernel.
+template <int N>
+struct HermExtSrc {
+  const in_vec2* __restrict__ xb;  // [rows][N/2+1]
+  int valid_o;
+  __device__ __forceinline__ float2 load(int o, int i, int) const {
+    if (o >= valid_o) return make_float2(0.f, 0.f);
+    constexpr int BINS = N / 2 + 1;
+    const in_vec2 v = __ldg(&xb[(long long)o * BINS + (i < BINS ? i : N - i)]);
+    return make_float2((float)v.x, i < BINS ? (float)v.y : -(float)v.y);
+  }
+};
+struct RealDst {
+  float* __restrict__ base;
+  int n;
+  int valid_o;
+  __device__ __forceinline__ void store(int o, int i, int, float2 v) const {
+    if (o < valid_o) base[(long long)o * n + i] = v.x;
+  }
+};
+template <int N, class RL, int C, int NT>
+__global__ void __launch_bounds__(NT) rows_c2r_odd_kernel(const __grid_constant__ HalfArgs a) {
+  static_assert(N % 2 == 1, "odd lengths only");
+  extern __shared__ __align__(16) float2 smem_f2[];
+  constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
+  const long long row0 = (long long)blockIdx.x * C;
+  const int valid = (int)min((long long)C, a.nrows - row0);
+  HermExtSrc<N> src{reinterpret_cast<const in_vec2*>(a.in) + row0 * (N / 2 + 1), valid};
+  RealDst dst{reinterpret_cast<float*>(a.out) + row0 * N, N, valid};
+  run_axis<RL, N, C, 1, NT, true, RowLayoutN<N>::template type>(src, dst, smem_f2, smem_f2 + BUF, a.tw, a.scale, true);
 }
 template <int H, class RL, int C>
 constexpr size_t rows_r2c_smem_bytes() {
@@ -606,7 +634,7 @@ constexpr size_t rows_r2c_smem_bytes() {
 template <int H, class RL, int C>
 constexpr size_t rows_c2r_smem_bytes() {
   constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
-  return sizeof(float2) * ((size_t)EX * 2 + (size_t)C * (H + 1));
+  return sizeof(float2) * (size_t)EX * (RL::count > 2 ? 2 : 1);
 }
 
 struct ColsArgs {
@@ -672,8 +700,9 @@ __global__ void __launch_bounds__(NT) cols_scatter_kernel(const __grid_constant_
   constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + BUF;
-  const long long o = blockIdx.x / a.tiles_per_outer;
-  const long long c0 = (long long)(blockIdx.x - o * a.tiles_per_outer) * CW;
+  const unsigned bid = a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const long long o = bid / a.tiles_per_outer;
+  const long long c0 = (long long)(bid - o * a.tiles_per_outer) * CW;
   const long long base = o * N * a.inner + c0;
   const int valid_c = (int)min((long long)CW, a.inner - c0);
   GlobalSrc<false> src{reinterpret_cast<const float2*>(a.in) + base, 0, a.inner, 1, valid_c};

@@ -160,7 +160,8 @@ namespace {
 struct FastPass : Pass {
   const Variant* v = nullptr;
   HalfMode half = HALF_NONE;
-  enum R2CMode { R2C_SMEM = 0, R2C_REG = 1, R2C_ODD = 2 } r2c_mode = R2C_SMEM;  // which R2C kernel (fast.cuh)
+  enum R2CMode { R2C_SMEM = 0, R2C_REG = 1, R2C_ODD = 2 } r2c_mode = R2C_SMEM;  // which R2C kernel (fast.cuh); R2C_ODD also
+                                                                                // marks the odd-length C2R
   float2* d_tw2 = nullptr;
   AxisView view;
   bool inverse = false, real_in = false, do_scale = false;
@@ -193,6 +194,7 @@ struct FastPass : Pass {
       if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many row tiles");
       if (half == HALF_R2C && r2c_mode == R2C_REG) v->launch_r2c_reg(a, (unsigned)grid, stream);
       else if (half == HALF_R2C && r2c_mode == R2C_ODD) v->launch_r2c_odd(a, (unsigned)grid, v->smem, stream);
+      else if (half == HALF_C2R && r2c_mode == R2C_ODD) v->launch_c2r_odd(a, (unsigned)grid, v->smem, stream);
       else v->launch_half(half == HALF_C2R, a, (unsigned)grid, stream);
     } else if (v->kind == ROWS) {
       RowsArgs a;
@@ -252,7 +254,7 @@ struct FastPass : Pass {
     a.tiles_per_outer = (int)((view.inner + v->tile - 1) / v->tile);
     a.scale = scale;
     a.do_scale = do_scale;
-    a.reverse = 0;
+    a.reverse = reverse_order ? 1 : 0;
     ScatterArgs sa;
     for (int i = 0; i < 16; ++i) sa.peer[i] = i < sc.npeers ? reinterpret_cast<float2*>(sc.peer_out[i]) : nullptr;
     sa.yl = (int)(view.n / sc.npeers);
@@ -286,11 +288,13 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   const AxisSpec& ax = p.axes[axis];
 
   std::vector<const Variant*> cands;
-  const bool odd_r2c = half == HALF_R2C && kind == ROWS && view.n % 2 == 1;
+  const bool odd_r2c = half != HALF_NONE && kind == ROWS && view.n % 2 == 1;  // (both directions of an odd half-spectrum axis)
   if (odd_r2c) {
-    // odd n: the n-point row variant itself on real input, storing bins 0..n/2 (C2R of odd n stays on the rt tier)
+    // odd n: the n-point row variant itself — R2C on real input storing bins 0..n/2, C2R on the Hermitian-extended row
+    if (src.dtype != B200FFT_F32) return nullptr;
     for (const Variant& v : registry())
-      if (v.kind == ROWS && v.n == (int)view.n && v.launch_r2c_odd && can_group(ax.ordered, v.radices)) cands.push_back(&v);
+      if (v.kind == ROWS && v.n == (int)view.n && v.launch_r2c_odd && v.launch_c2r_odd && can_group(ax.ordered, v.radices))
+        cands.push_back(&v);
   } else if (half != HALF_NONE) {
     if (kind != ROWS || view.n % 2) return nullptr;
     const auto reduced = drop_factor_two(ax.ordered);
@@ -356,7 +360,8 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   pass->scale = scale_inverse ? (float)(1.0 / (double)view.n) : 1.f;
   pass->half = half;
   pass->r2c_mode = odd_r2c ? FastPass::R2C_ODD : r2c_reg ? FastPass::R2C_REG : FastPass::R2C_SMEM;
-  if (odd_r2c) pass->real_in = true;
+  if (odd_r2c) pass->real_in = half == HALF_R2C;
+  if (odd_r2c && half == HALF_C2R) pass->scale = (float)(1.0 / (double)view.n);
   if (half != HALF_NONE && !odd_r2c) {
     if (half == HALF_C2R) pass->scale = (float)(1.0 / (double)view.n);  // 1/(2H): the inverse is always normalised
     std::vector<float2> tw2 = build_half_twiddles(view.n, half == HALF_C2R);
@@ -364,7 +369,7 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
     plan.owned_device.push_back(pass->d_tw2);
     if (cudaMemcpy(pass->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
   }
-  std::vector<float2> tw = build_twiddles(v->radices, half == HALF_NONE ? pass->inverse : half == HALF_C2R);
+  std::vector<float2> tw = build_twiddles(v->radices, half == HALF_NONE ? pass->inverse : half == HALF_C2R);  // (C2R: inverse tables)
   if (cudaMalloc(&pass->d_tw, tw.size() * sizeof(float2)) != cudaSuccess) return nullptr;
   plan.owned_device.push_back(pass->d_tw);  // owned by the plan BEFORE the copy: a failed copy must not leak it
   if (cudaMemcpy(pass->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
@@ -372,8 +377,10 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
   for (uint32_t r : ax.ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
   char buf[320];
   if (odd_r2c)
-    snprintf(buf, sizeof buf, "axis %d: r2c-odd[%s] n=%lld (real rows, bins 0..n/2 stored) smem=%zuB user stages=[%s] fused as (%s)",
-             axis, v->name.c_str(), (long long)view.n, v->smem, stages.c_str(), radix_name(v->radices).c_str());
+    snprintf(buf, sizeof buf, "axis %d: %s[%s] n=%lld (%s) smem=%zuB user stages=[%s] fused as (%s)", axis,
+             half == HALF_R2C ? "r2c-odd" : "c2r-odd", v->name.c_str(), (long long)view.n,
+             half == HALF_R2C ? "real rows, bins 0..n/2 stored" : "Hermitian-extended load, real rows stored", v->smem, stages.c_str(),
+             radix_name(v->radices).c_str());
   else if (half != HALF_NONE)
     snprintf(buf, sizeof buf, "axis %d: %s[%s] n=%lld (as %d complex) smem=%zuB user stages=[%s] fused as (2)(%s)", axis,
              half == HALF_R2C ? (r2c_reg ? "r2c-reg" : "r2c") : "c2r", v->name.c_str(), (long long)view.n, v->n,

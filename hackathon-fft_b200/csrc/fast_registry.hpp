@@ -38,6 +38,8 @@ struct Variant {
   // odd n: half-spectrum R2C of length n itself (real rows in, bins 0..n/2 out) on this n-point variant
   void (*launch_r2c_odd)(const HalfArgs&, unsigned, size_t, cudaStream_t) = nullptr;
   cudaError_t (*prepare_r2c_odd)(size_t) = nullptr;
+  // ... and its inverse: rows of n/2+1 bins in, Hermitian-extended on load, real rows out
+  void (*launch_c2r_odd)(const HalfArgs&, unsigned, size_t, cudaStream_t) = nullptr;
 };
 
 std::vector<Variant>& registry();
@@ -110,9 +112,14 @@ struct HalfOddV {
   static void launch(const HalfArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
     rows_r2c_odd_kernel<N, RL, C, NT><<<grid, NT, smem, st>>>(a);
   }
+  static void launch_c2r(const HalfArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    rows_c2r_odd_kernel<N, RL, C, NT><<<grid, NT, smem, st>>>(a);
+  }
   static cudaError_t prepare(size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(rows_r2c_odd_kernel<N, RL, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rows_r2c_odd_kernel<N, RL, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(rows_c2r_odd_kernel<N, RL, C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e;
   }
 };
 
@@ -204,6 +211,7 @@ void reg_rows_impl() {
     }
     if constexpr (N % 2 == 1) {
       v.launch_r2c_odd = &HalfOddV<N, RL, C, NT>::launch;
+      v.launch_c2r_odd = &HalfOddV<N, RL, C, NT>::launch_c2r;
       v.prepare_r2c_odd = &HalfOddV<N, RL, C, NT>::prepare;
     }
   }

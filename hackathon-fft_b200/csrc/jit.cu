@@ -131,6 +131,7 @@ enum JitKind {
   JIT_R2C_REG,      // rows_r2c_reg_kernel<H, RL, C, NT>: Hermitian unpack in registers (warp shuffles)
   JIT_R2C_ODD,      // rows_r2c_odd_kernel<N, RL, C, NT>: odd n, the n-point row kernel on real rows, bins 0..n/2 stored
   JIT_C2R,          // rows_c2r_kernel<H, RL, C, NT>: Hermitian pack fused into stage 0 of the H-point inverse
+  JIT_C2R_ODD,      // rows_c2r_odd_kernel<N, RL, C, NT>: odd n, Hermitian-extended load, real rows stored
   // long axes as two passes, N = N1 * N2 (fast.cuh, "four-step"):
   JIT_SPLIT_A,      // cols_split_a_kernel<N1, RL, CW, NT, INV>: N1-point strided transforms, W_N^{k1 n2} fused into the store
   JIT_SPLIT_B_COLS, // cols_split_b_kernel<N2, RL, CW, NT, INV>: N2-point strided transforms, natural-order store
@@ -168,6 +169,7 @@ struct JitSpec {
       case JIT_R2C: return "b200fft::rows_r2c_kernel<" + head + ">";
       case JIT_R2C_REG: return "b200fft::rows_r2c_reg_kernel<" + head + ">";
       case JIT_R2C_ODD: return "b200fft::rows_r2c_odd_kernel<" + head + ">";
+      case JIT_C2R_ODD: return "b200fft::rows_c2r_odd_kernel<" + head + ">";
       case JIT_SPLIT_A: return "b200fft::cols_split_a_kernel<" + head + ", " + inv + ">";
       case JIT_SPLIT_B_COLS: return "b200fft::cols_split_b_kernel<" + head + ", " + inv + ">";
       case JIT_SPLIT_B_ROWS: return "b200fft::rows_split_b_kernel<" + head + ", " + inv + ">";
@@ -178,6 +180,7 @@ struct JitSpec {
     switch (kind) {
       case JIT_ROWS:
       case JIT_SPLIT_B_ROWS:
+      case JIT_C2R_ODD:
       case JIT_R2C_ODD: return "b200fft::rows_smem_bytes<" + shape_args() + ">()";
       case JIT_COLS:
       case JIT_SPLIT_A:
@@ -189,7 +192,7 @@ struct JitSpec {
     }
   }
   std::string name() const {
-    static const char* const tag[] = {"jitrows", "jitcols", "jitscatter", "jitr2c", "jitr2creg", "jitr2codd", "jitc2r",
+    static const char* const tag[] = {"jitrows", "jitcols", "jitscatter", "jitr2c", "jitr2creg", "jitr2codd", "jitc2r", "jitc2rodd",
                                       "jitsplitA", "jitsplitBcols", "jitsplitBrows"};
     return std::string(tag[kind]) + std::to_string(n) + "_" + radix_name(radices) + (strided() ? "_w" : "_c") + std::to_string(tile) +
            "_t" + std::to_string(threads) + (f64 ? "_f64" : "") + (in_dtype == B200FFT_U8 ? "_inu8" : in_dtype == (f64 ? B200FFT_F32 : B200FFT_F64) ? (f64 ? "_inf32" : "_inf64") : "");
@@ -223,7 +226,6 @@ struct JitSpec {
     const size_t pingpong = radices.size() > 2 ? 2 : 1;
     switch (kind) {
       case JIT_R2C: return esz() * (size_t)std::max<long long>(ex, (long long)tile * n) * 2;
-      case JIT_C2R: return esz() * ((size_t)ex * 2 + (size_t)tile * (n + 1));
       default: return esz() * (size_t)ex * pingpong;
     }
   }
@@ -277,6 +279,13 @@ int compile(const JitSpec& spec, std::vector<char>* cubin, std::string* lowered,
   rtc.DestroyProgram(&prog);
   if (rc) return fail(B200FFT_ERR_CUDA, "nvrtcGetCUBIN: %s", rtc.GetErrorString(rc));
   *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (const char* dir = getenv("B200FFT_JIT_DUMP_DIR")) {  // keep the cubin (cuobjdump -sass <file>: profiles/sass/)
+    const std::string path = std::string(dir) + "/" + spec.name() + ".cubin";
+    if (FILE* f = fopen(path.c_str(), "wb")) {
+      fwrite(cubin->data(), 1, cubin->size(), f);
+      fclose(f);
+    }
+  }
   return B200FFT_OK;
 }
 
@@ -501,7 +510,7 @@ struct JitPass : Pass {
     ca.tiles_per_outer = (int)((view.inner + spec.tile - 1) / spec.tile);
     ca.scale = scale;
     ca.do_scale = do_scale;
-    ca.reverse = (dst != nullptr && reverse_order) ? 1 : 0;  // (dst == nullptr: the scattering store keeps the forward order)
+    ca.reverse = reverse_order ? 1 : 0;
     return ca;
   }
   template <class A, class T2>
@@ -624,8 +633,7 @@ bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, 
   } else {
     if (view.inner != 1) return false;  // half-spectrum handling is a row pass
     if (view.n % 2) {
-      if (half != HALF_R2C) return false;  // C2R of odd lengths stays on the runtime-length tier
-      spec->kind = JIT_R2C_ODD;
+      spec->kind = half == HALF_R2C ? JIT_R2C_ODD : JIT_C2R_ODD;
       spec->n = (int)view.n;
       if (!jit_group(ax.ordered, &spec->radices, f64)) return false;
     } else {
@@ -839,7 +847,7 @@ std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView
     plan.owned_device.push_back(*d);  // owned by the plan before the copy: a failed copy must not leak it
     return cudaMemcpy(*d, data, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
-  const bool need_tw2 = half != HALF_NONE && spec.kind != JIT_R2C_ODD;
+  const bool need_tw2 = half != HALF_NONE && spec.kind != JIT_R2C_ODD && spec.kind != JIT_C2R_ODD;
   if (f64) {
     const std::vector<double2> tw = stage_twiddles64(spec.radices, spec.inverse);
     if (!upload(tw.data(), tw.size() * sizeof(double2), &pass->d_tw)) return nullptr;
@@ -860,9 +868,9 @@ std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView
   char buf[400];
   snprintf(buf, sizeof buf, "axis %d: %s n=%lld inner=%lld smem=%zuB regs=%d user stages=[%s] fused as %s(%s)%s [NVRTC, %.0f ms]", axis,
            spec.name().c_str(), (long long)view.n, (long long)view.inner, pass->smem, k->regs, stages.c_str(),
-           half != HALF_NONE && spec.kind != JIT_R2C_ODD ? "(2)" : "", radix_name(spec.radices).c_str(),
+           need_tw2 ? "(2)" : "", radix_name(spec.radices).c_str(),
            half == HALF_R2C ? (spec.kind == JIT_R2C_ODD ? " r2c (real rows, bins 0..n/2 stored)" : " r2c")
-           : half == HALF_C2R ? " c2r" : spec.real_in ? " real-in" : "",
+           : half == HALF_C2R ? (spec.kind == JIT_C2R_ODD ? " c2r (Hermitian-extended load)" : " c2r") : spec.real_in ? " real-in" : "",
            k->compile_ms);
   pass->text = buf;
   return pass;

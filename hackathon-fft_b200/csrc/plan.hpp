@@ -86,6 +86,11 @@ struct b200fft_plan {
   int64_t group_mult = 1;         // group units per batch item = prod(dims outside the group)
   int64_t group_chunk_units = 0;
   size_t group_in_stride = 0, group_out_stride = 0;  // bytes per unit
+  // pipelined group execution (api.cu: run_passes): the group's first pass runs on the caller's stream, the others on
+  // this side stream one chunk behind, so the two kernels overlap and the chunk between them never leaves L2
+  cudaStream_t group_stream = nullptr;
+  cudaEvent_t group_ev[4] = {};  // fork, first-pass-done, tail[2]
+  bool group_pipeline = false;
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   size_t work_stride = 0;     // workspace bytes per batch item

@@ -154,3 +154,24 @@ def test_unregistered_lengths_use_the_rt_tier(monkeypatch):
         assert np.linalg.norm(c2(got) - want) <= 2e-6 * np.sqrt(len(shape) - 1) * np.linalg.norm(want)
         back, _ = c2r(got, shape[-1])
         assert np.linalg.norm(back[..., 0] - x[..., 0]) <= 4e-6 * np.linalg.norm(x)
+
+
+def test_odd_c2r_on_the_compile_time_kernel():
+    """C2R of an odd length with a registered row variant (93 = 31 x 3): the n-point inverse on the Hermitian-extended
+    row (rows_c2r_odd_kernel), no longer the runtime-length tier."""
+    import torch
+    rng = np.random.default_rng(8)
+    for shape in ((64, 93), (5, 12, 93)):
+        real = rng.standard_normal(shape)
+        axes = tuple(range(1, len(shape)))
+        spec = np.fft.rfftn(real, axes=axes)
+        x = np.stack([spec.real, spec.imag], axis=-1).astype(np.float32)
+        plan = b200fft.plan_fft("float32", "float32", x.shape, shape + (1,), real_mode=b200fft.REAL_HALF, inverse=True)
+        desc = plan.describe()
+        assert "c2r-odd[rows93" in desc and "rt_" not in desc and "generic" not in desc, desc
+        out = torch.full(shape + (1,), float("nan"), device="cuda")
+        b200fft.fft(out, torch.from_numpy(x).cuda(), plan=plan)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()[..., 0].astype(np.float64)
+        assert np.linalg.norm(got - real) <= 2e-6 * np.sqrt(len(axes)) * np.linalg.norm(real), desc
+        plan.destroy()

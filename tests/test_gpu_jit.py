@@ -107,6 +107,8 @@ HALF_CASES = [
     ((40, 1000), False), ((40, 1000), True),
     ((64, 200), False), ((64, 200), True),
     ((30, 243), False),                       # odd length: the n-point row kernel on real rows
+    ((30, 243), True),                        # ... and its inverse: Hermitian-extended load, real rows stored
+    ((4, 10, 75), True),
     ((7, 50, 600), False), ((7, 50, 600), True),
     ((3, 12, 10, 100), False), ((3, 12, 10, 100), True),
     ((9, 6), False), ((9, 6), True),
@@ -137,8 +139,7 @@ def test_jit_half_spectrum(shape, inverse):
         x = np.stack([spec.real, spec.imag], axis=-1).astype(np.float32)
         plan = b200fft.plan_fft("float32", "float32", cshape + (2,), shape + (1,), real_mode=b200fft.REAL_HALF, inverse=True)
         desc = plan.describe()
-        if shape[-1] % 2 == 0:
-            assert "jitc2r" in desc and "generic" not in desc, desc
+        assert "jitc2r" in desc and "generic" not in desc and "rt_" not in desc, desc
         out = torch.full(shape + (1,), float("nan"), device="cuda")
         b200fft.fft(out, torch.from_numpy(x).cuda(), plan=plan)
         torch.cuda.synchronize()

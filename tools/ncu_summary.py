@@ -38,7 +38,10 @@ SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "us
 
 
 def read_report(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):  # the raw page already exported on the GPU box (`ncu -i rep --page raw --csv`)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     launches = []
@@ -68,6 +71,14 @@ def main():
     for spec in sys.argv[2:]:
         name, rest = spec.split("=", 1)
         path, _, alg = rest.partition(":")
+        if name.startswith("plan:"):
+            # every launch of ONE exec of a plan (captured with --cache-control none, so what one pass leaves in L2 is there
+            # for the next): their DRAM bytes summed = the traffic of the whole transform; bench.py's shapes[] rows read it
+            ls = read_report(path)
+            tot = sum(d.get("dram_read", 0) + d.get("dram_write", 0) for d in ls)
+            traffic[name] = {"dram_bytes_per_exec": tot, "algorithmic_bytes_per_exec": float(alg) if alg else None,
+                             "launches": len(ls), "kernels": [d["kernel"].strip()[:160] for d in ls],
+                             "time_us_under_ncu": sum(d.get("time", 0) for d in ls) * 1e6, "source": os.path.basename(path)}
         for d in read_report(path):
             tr = d.get("dram_read", 0) + d.get("dram_write", 0)
             ratio = "%.3f" % (tr / float(alg)) if alg else "-"
