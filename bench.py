@@ -460,6 +460,74 @@ def bench_slab(n, world, rank, torch, dist, steps=10, warmup=3):
     return res
 
 
+def bench_mgpu(world, shape, torch, b200fft):
+    """N > 1, rank 0 only (the other ranks idle at a barrier): the SAME job through the C ABI's single-process multi-device
+    entry points (b200fft_mgpu_*, include/b200fft.h) — what a Mojo / C host without torch.distributed would call.
+    (a) end to end: world x per-GPU batch from ONE pinned host array, one host thread + 3-stream pipeline per device;
+    (b) the 512^3 slab transform with device-resident slabs (peer-to-peer scattering stores + event barrier)."""
+    res = {"api": "b200fft_mgpu_plan_create / exec / exec_host, one process driving %d devices" % world}
+    try:
+        devs = list(range(world))
+        B = shape[0] * world
+        lay = (B,) + tuple(shape[1:]) + (2,)
+        plan = b200fft.MgpuPlan("float32", "float32", lay, lay, devices=devs, mode=b200fft.MGPU_BATCH_SHARD)
+        h_in = torch.empty(lay, dtype=torch.float32).pin_memory()
+        h_in[:shape[0]].normal_()
+        for g in range(1, world):
+            h_in[g * shape[0]:(g + 1) * shape[0]].copy_(h_in[:shape[0]])
+        h_out = torch.empty(lay, dtype=torch.float32).pin_memory()
+        plan.exec_host(h_out.numpy(), h_in.numpy())
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            plan.exec_host(h_out.numpy(), h_in.numpy())
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+        k = 4
+        want = torch.fft.fft(torch.view_as_complex(h_in[-k:].double().contiguous()), dim=1)
+        got = torch.view_as_complex(h_out[-k:].double().contiguous())
+        res["e2e_batch_shard"] = {"ms_per_step": best, "value": world * flops_c2c(shape) / best / 1e6, "unit": "GFLOP/s",
+                                  "h2d_bytes_per_step": int(h_in.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4),
+                                  "rel_l2_vs_torch_f64_last_rows": float((got - want).norm() / want.norm())}
+        plan.destroy()
+        del h_in, h_out
+    except Exception as ex:
+        res["e2e_batch_shard"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    try:
+        n = 512
+        zl = yl = n // world
+        lay = (1, n, n, n, 2)
+        plan = b200fft.MgpuPlan("float32", "float32", lay, lay, devices=devs, mode=b200fft.MGPU_SLAB)
+        ins = [torch.randn((zl, n, n, 2), device="cuda:%d" % d) for d in devs]
+        outs = [torch.empty((n, yl, n, 2), device="cuda:%d" % d) for d in devs]
+        streams = [torch.cuda.ExternalStream(plan.stream(i), device="cuda:%d" % d) for i, d in enumerate(devs)]
+        for _ in range(3):
+            plan.exec(outs, ins)
+        plan.synchronize()
+        ev = []
+        for i, d in enumerate(devs):
+            with torch.cuda.device(d):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(streams[i])
+                ev.append((e0, e1))
+        steps = 10
+        for _ in range(steps):
+            plan.exec(outs, ins)
+        for i, d in enumerate(devs):
+            with torch.cuda.device(d):
+                ev[i][1].record(streams[i])
+        plan.synchronize()
+        ms = max(a.elapsed_time(b) for a, b in ev) / steps
+        # parity: Parseval over all devices + one sampled output bin by direct summation in float64
+        e_in = sum(float(t.double().pow(2).sum()) for t in ins)
+        e_out = sum(float(t.double().pow(2).sum()) for t in outs)
+        res["slab_512"] = {"ms": ms, "gflops": 5.0 * n ** 3 * math.log2(n ** 3) / ms / 1e6,
+                           "parseval_rel_err": abs(e_out / (e_in * n ** 3) - 1.0)}
+        plan.destroy()
+    except Exception as ex:
+        res["slab_512"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -625,6 +693,8 @@ def main():
     del x, out
     plan.destroy()
     torch.cuda.empty_cache()
+    if dist and world > 1:
+        line["mgpu_single_process"] = bench_mgpu(world, shape, torch, b200fft)
 
     if not args.no_shapes and world == 1:
         line["shapes"] = [bench_shape(n, s, r, torch, b200fft, max(5, min(args.steps, 20)), 3, peak)

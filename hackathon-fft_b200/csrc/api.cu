@@ -484,8 +484,8 @@ int b200fft_exec(b200fft_plan* plan, void* d_out, const void* d_in, void* cu_str
   return run_passes(plan, d_out, d_in, plan->prob.batch, (cudaStream_t)cu_stream);
 }
 
-int b200fft_exec_scatter(b200fft_plan* plan, void* const* peer_out, int npeers, int my_rank, const void* d_in,
-                         void* d_work, void* cu_stream) {
+static int exec_scatter_impl(b200fft_plan* plan, void* const* peer_out, int npeers, int my_rank, long long zbase, const void* d_in,
+                             void* d_work, void* cu_stream) {
   if (!plan || !peer_out || !d_in || !d_work) return fail(B200FFT_ERR_INVALID_ARG, "null plan or buffer");
   if (plan->prob.half) return fail(B200FFT_ERR_UNSUPPORTED, "exec_scatter takes a complex plan");
   if (my_rank < 0 || my_rank >= npeers) return fail(B200FFT_ERR_INVALID_ARG, "my_rank %d outside 0..%d", my_rank, npeers);
@@ -505,7 +505,20 @@ int b200fft_exec_scatter(b200fft_plan* plan, void* const* peer_out, int npeers, 
   sc.peer_out = peer_out;
   sc.npeers = npeers;
   sc.my_rank = my_rank;
-  return last.launch_scatter(last.src_sel == BUF_INPUT ? d_in : (const void*)d_work, sc, plan->prob.batch, st);
+  sc.zbase = zbase;
+  // a one-pass plan (only the split axis transformed) scatters straight from d_in
+  return last.launch_scatter(n == 1 || last.src_sel == BUF_INPUT ? d_in : (const void*)d_work, sc, plan->prob.batch, st);
+}
+
+int b200fft_exec_scatter(b200fft_plan* plan, void* const* peer_out, int npeers, int my_rank, const void* d_in,
+                         void* d_work, void* cu_stream) {
+  return exec_scatter_impl(plan, peer_out, npeers, my_rank, -1, d_in, d_work, cu_stream);
+}
+
+int b200fft_exec_scatter_at(b200fft_plan* plan, void* const* peer_out, int npeers, int64_t z_first, const void* d_in,
+                            void* d_work, void* cu_stream) {
+  if (z_first < 0) return fail(B200FFT_ERR_INVALID_ARG, "negative plane offset");
+  return exec_scatter_impl(plan, peer_out, npeers, 0, (long long)z_first, d_in, d_work, cu_stream);
 }
 
 int b200fft_stream_synchronize(void* cu_stream) {

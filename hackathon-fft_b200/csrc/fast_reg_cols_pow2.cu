@@ -10,6 +10,7 @@ void register_cols_pow2() {
   reg_cols<512, 8, 256, true, 8, 8, 8>();
   reg_cols<512, 8, 128, false, 32, 16>();
   reg_cols<512, 16, 512, false, 32, 16>();
+  reg_cols<512, 32, 512, true, 32, 16>();  // 256-byte runs for the slab decomposition's remote stores (B200FFT_PREFER=_w32; r2_slab.md)
   reg_cols<1024, 8, 256, true, 32, 32>();
   // Tried and dropped: a 33-column tile for the middle pass of a 64^3 R2C (inner = 33 = the half spectrum of a 64-point real
   // axis, one contiguous 16.9 KB block per tile instead of 2 full 16-column tiles + 1 column): 100 x 64^3 R2C 0.1727 ms vs

@@ -259,7 +259,7 @@ struct FastPass : Pass {
     for (int i = 0; i < 16; ++i) sa.peer[i] = i < sc.npeers ? reinterpret_cast<float2*>(sc.peer_out[i]) : nullptr;
     sa.yl = (int)(view.n / sc.npeers);
     const long long outer = nbatch * view.outer_per_batch;
-    sa.zbase = (long long)sc.my_rank * outer;
+    sa.zbase = sc.zbase >= 0 ? sc.zbase : (long long)sc.my_rank * outer;
     const long long grid = outer * a.tiles_per_outer;
     if (grid <= 0) return B200FFT_OK;
     if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many column tiles");

@@ -571,7 +571,7 @@ struct JitPass : Pass {
     for (int i = 0; i < 16; ++i) sa.peer[i] = i < sc.npeers ? reinterpret_cast<float2*>(sc.peer_out[i]) : nullptr;
     sa.yl = (int)(view.n / sc.npeers);
     const long long outer = nbatch * view.outer_per_batch;
-    sa.zbase = (long long)sc.my_rank * outer;
+    sa.zbase = sc.zbase >= 0 ? sc.zbase : (long long)sc.my_rank * outer;
     if (spec.f64) {
       ColsArgs64 ca = cols_args<ColsArgs64, double2>(src, nullptr);
       void* params[2] = {&ca, &sa};

@@ -14,8 +14,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -41,6 +44,12 @@ struct Slot {
   b200fft_plan* planz = nullptr; // SLAB: Z pass over the received [Z][Y/G][X] slab
   cudaStream_t stream = nullptr;
   cudaEvent_t scattered = nullptr, done = nullptr;
+  // SLAB with chunks > 1: the slot's planes in `chunks` pieces; X pass of piece c+1 (stream) overlaps the NVLink-bound
+  // scattering Y pass of piece c (stream2)
+  b200fft_plan* planx = nullptr;  // X rows of one piece (axis 1 only)
+  b200fft_plan* plany = nullptr;  // Y pass of one piece (axis 0 only): its single pass is the scattering one
+  cudaStream_t stream2 = nullptr;
+  std::vector<cudaEvent_t> xdone;
   void* work = nullptr;          // SLAB: [Z/G][Y][X] intermediate of step 1
   void* h_in = nullptr;          // SLAB exec_host: device staging, allocated on first use
   void* h_out = nullptr;
@@ -49,12 +58,30 @@ struct Slot {
 
 }  // namespace
 
+struct MgpuPool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<uint64_t> gen{0};
+  std::atomic<int> arrived{0};
+  std::atomic<bool> stop{false};
+  void* const* out_tab = nullptr;
+  const void* const* in_tab = nullptr;
+  std::vector<int> rc;
+  std::vector<std::string> msg;
+  void start(b200fft_mgpu_plan* plan, int n);
+  int run(int n, void* const* d_out, const void* const* d_in);
+  void shutdown();
+};
+
 struct b200fft_mgpu_plan {
+  std::unique_ptr<MgpuPool> pool;  // enqueue workers (B200FFT_MGPU_THREADS=0: enqueue from the calling thread)
   int mode = 0;
   int64_t batch = 0;
   int64_t Z = 0, Y = 0, X = 0;
   size_t in_item = 0, out_item = 0;  // BATCH_SHARD: bytes per batch item
   bool executed = false;             // SLAB: `done` events have been recorded at least once
+  int chunks = 1;                    // SLAB: pieces per slot (B200FFT_MGPU_SLAB_CHUNKS)
   std::vector<Slot> slots;
   std::string text;
 };
@@ -123,15 +150,22 @@ int b200fft_mgpu_split(int64_t batch, int ngpu, int g, int64_t* first, int64_t* 
 
 int b200fft_mgpu_plan_destroy(b200fft_mgpu_plan* m) {
   if (!m) return B200FFT_OK;
+  if (m->pool) m->pool->shutdown();
   DevGuard guard;
   for (Slot& s : m->slots) {
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.stream2) cudaStreamSynchronize(s.stream2);
   }
   for (Slot& s : m->slots) {
     cudaSetDevice(s.device);
     if (s.plan) b200fft_plan_destroy(s.plan);
     if (s.planz) b200fft_plan_destroy(s.planz);
+    if (s.planx) b200fft_plan_destroy(s.planx);
+    if (s.plany) b200fft_plan_destroy(s.plany);
+    for (cudaEvent_t e : s.xdone)
+      if (e) cudaEventDestroy(e);
+    if (s.stream2) cudaStreamDestroy(s.stream2);
     for (void* p : {s.work, s.h_in, s.h_out})
       if (p) cudaFree(p);
     if (s.scattered) cudaEventDestroy(s.scattered);
@@ -203,6 +237,12 @@ int b200fft_mgpu_plan_create(b200fft_mgpu_plan** out, const b200fft_desc* desc, 
     const int64_t zl = m->Z / ngpu, yl = m->Y / ngpu;
     if (yl < 2 && ngpu > 1) return bail(fail(B200FFT_ERR_INVALID_ARG, "fewer than 2 y rows per device"));
     if (int rc = enable_peers(m->slots)) return bail(rc);
+    // Pieces per slot: measured on 8 B200 (profiles/r2_slab.md). The Y pass is bound by its NVLink stores, so the SMs have
+    // room for the next piece's X pass while it runs.
+    int chunks = 1;
+    if (const char* e = getenv("B200FFT_MGPU_SLAB_CHUNKS")) chunks = std::max(1, atoi(e));
+    while (chunks > 1 && zl % chunks) --chunks;
+    m->chunks = chunks;
     std::vector<uint32_t> b_yx, b_z;
     std::vector<int32_t> c_yx, c_z;
     slice_bases(*desc, 1, 3, &b_yx, &c_yx);
@@ -236,6 +276,14 @@ int b200fft_mgpu_plan_create(b200fft_mgpu_plan** out, const b200fft_desc* desc, 
       dz.bases = cz3.empty() ? nullptr : b_z.data();
       dz.bases_count = cz3.empty() ? nullptr : cz3.data();
       if (int rc = b200fft_plan_create(&s.planz, &dz)) return bail(rc);
+      if (m->chunks > 1) {
+        b200fft_desc dx = d2, dy = d2;
+        dx.batch = dy.batch = zl / m->chunks;
+        dx.axis_mask = 2;  // axis 1 = X
+        dy.axis_mask = 1;  // axis 0 = Y
+        if (int rc = b200fft_plan_create(&s.planx, &dx)) return bail(rc);
+        if (int rc = b200fft_plan_create(&s.plany, &dy)) return bail(rc);
+      }
       if (cudaSetDevice(s.device) != cudaSuccess || cudaMalloc(&s.work, s.in_bytes) != cudaSuccess) {
         cudaGetLastError();
         return bail(fail(B200FFT_ERR_ALLOC, "cannot allocate %zu B of slab workspace on device %d", s.in_bytes, s.device));
@@ -245,18 +293,30 @@ int b200fft_mgpu_plan_create(b200fft_mgpu_plan** out, const b200fft_desc* desc, 
   for (Slot& s : m->slots) {
     if (cudaSetDevice(s.device) != cudaSuccess || cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.scattered, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess ||
+        (m->chunks > 1 && cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking) != cudaSuccess)) {
       cudaError_t e = cudaGetLastError();
       return bail(fail(B200FFT_ERR_CUDA, "stream / event creation on device %d: %s", s.device, cudaGetErrorString(e)));
     }
   }
-  char head[256];
+  if (m->chunks > 1)
+    for (Slot& s : m->slots) {
+      cudaSetDevice(s.device);
+      s.xdone.assign((size_t)m->chunks, nullptr);
+      for (auto& e : s.xdone)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+          cudaGetLastError();
+          return bail(fail(B200FFT_ERR_CUDA, "event creation on device %d", s.device));
+        }
+    }
+  char head[320];
   if (mode == B200FFT_MGPU_BATCH_SHARD)
     snprintf(head, sizeof head, "mgpu batch-shard over %d devices, batch %lld, no communication\n", ngpu, (long long)m->batch);
   else
     snprintf(head, sizeof head,
-             "mgpu slab %lldx%lldx%lld over %d devices: local (Y,X) + peer-to-peer scattering Y stores -> event barrier -> Z pass\n",
-             (long long)m->Z, (long long)m->Y, (long long)m->X, ngpu);
+             "mgpu slab %lldx%lldx%lld over %d devices: local (Y,X) + peer-to-peer scattering Y stores -> event barrier -> Z pass%s\n",
+             (long long)m->Z, (long long)m->Y, (long long)m->X, ngpu,
+             m->chunks > 1 ? (" [" + std::to_string(m->chunks) + " pieces per device: X of piece c+1 overlaps the scattering Y pass of piece c]").c_str() : "");
   m->text = head;
   for (int g = 0; g < ngpu; ++g) {
     const Slot& s = m->slots[(size_t)g];
@@ -272,6 +332,13 @@ int b200fft_mgpu_plan_create(b200fft_mgpu_plan** out, const b200fft_desc* desc, 
         describe_plan(s.planz, &t);
         m->text += t;
       }
+    }
+  }
+  {
+    const char* e = getenv("B200FFT_MGPU_THREADS");
+    if (ngpu > 1 && !(e && atoi(e) == 0)) {
+      m->pool.reset(new MgpuPool());
+      m->pool->start(m.get(), ngpu);
     }
   }
   *out = m.release();
@@ -306,41 +373,128 @@ size_t b200fft_mgpu_describe(const b200fft_mgpu_plan* m, char* buf, size_t cap) 
   return m->text.size() + 1;
 }
 
+// One slot's share of an exec call. phase 0: everything up to (and including) the record of `scattered`; phase 1: the Z
+// pass. Between the two every slot must have RECORDED its `scattered` event, or a wait on it would be a no-op.
+static int slot_enqueue(b200fft_mgpu_plan* m, int g, int phase, void* const* d_out, const void* const* d_in) {
+  const int G = (int)m->slots.size();
+  Slot& s = m->slots[(size_t)g];
+  B200_CUDA_CHECK(cudaSetDevice(s.device));
+  if (m->mode == B200FFT_MGPU_BATCH_SHARD) return phase == 0 ? b200fft_exec(s.plan, d_out[g], d_in[g], s.stream) : B200FFT_OK;
+  if (phase == 0) {
+    // a slot may not start scattering call k+1 into a peer's slab while that peer still runs the Z pass of call k
+    if (m->executed)
+      for (int h = 0; h < G; ++h)
+        if (h != g) B200_CUDA_CHECK(cudaStreamWaitEvent(s.stream, m->slots[(size_t)h].done, 0));
+    if (m->chunks <= 1) {
+      if (int rc = b200fft_exec_scatter(s.plan, d_out, G, g, d_in[g], s.work, s.stream)) return rc;
+      B200_CUDA_CHECK(cudaSetDevice(s.device));
+      B200_CUDA_CHECK(cudaEventRecord(s.scattered, s.stream));
+    } else {
+      const int64_t zc = s.count / m->chunks;
+      const size_t piece = (size_t)zc * (size_t)m->Y * (size_t)m->X * 8;
+      for (int c = 0; c < m->chunks; ++c) {
+        char* work_c = (char*)s.work + (size_t)c * piece;
+        if (int rc = b200fft_exec(s.planx, work_c, (const char*)d_in[g] + (size_t)c * piece, s.stream)) return rc;
+        B200_CUDA_CHECK(cudaSetDevice(s.device));
+        B200_CUDA_CHECK(cudaEventRecord(s.xdone[(size_t)c], s.stream));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(s.stream2, s.xdone[(size_t)c], 0));
+        if (int rc = b200fft_exec_scatter_at(s.plany, d_out, G, s.first + c * zc, work_c, work_c, s.stream2)) return rc;
+        B200_CUDA_CHECK(cudaSetDevice(s.device));
+      }
+      B200_CUDA_CHECK(cudaEventRecord(s.scattered, s.stream2));
+    }
+    return B200FFT_OK;
+  }
+  for (int h = 0; h < G; ++h)
+    if (h != g || m->chunks > 1) B200_CUDA_CHECK(cudaStreamWaitEvent(s.stream, m->slots[(size_t)h].scattered, 0));
+  if (int rc = b200fft_exec(s.planz, d_out[g], d_out[g], s.stream)) return rc;
+  B200_CUDA_CHECK(cudaSetDevice(s.device));
+  B200_CUDA_CHECK(cudaEventRecord(s.done, s.stream));
+  return B200FFT_OK;
+}
+
+// Enqueue workers: one persistent host thread per slot. Issuing one exec to 8 devices from ONE thread costs ~100 driver
+// calls back to back (~0.3 ms: as long as the 512^3 slab transform itself takes on 8 GPUs); spread over the workers the
+// host side takes the time of one slot. Workers spin briefly for the next call before they sleep.
+void MgpuPool::start(b200fft_mgpu_plan* plan, int n) {
+  for (int g = 0; g < n; ++g)
+    threads.emplace_back([this, plan, g, n] {
+      uint64_t seen = 0;
+      for (;;) {
+        uint64_t cur = seen;
+        for (int spin = 0; spin < 20000 && (cur = gen.load(std::memory_order_acquire)) == seen; ++spin) {
+        }
+        if (cur == seen) {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return gen.load(std::memory_order_acquire) != seen; });
+          cur = gen.load(std::memory_order_acquire);
+        }
+        seen = cur;
+        if (stop.load()) return;
+        for (int phase = 0; phase < 2; ++phase) {
+          if (rc[(size_t)g] == B200FFT_OK) {
+            const int r = slot_enqueue(plan, g, phase, out_tab, in_tab);
+            if (r != B200FFT_OK) {
+              rc[(size_t)g] = r;
+              msg[(size_t)g] = last_error();
+            }
+          }
+          // phase barrier (also the completion signal after phase 1)
+          const int want = (phase + 1) * n;
+          arrived.fetch_add(1, std::memory_order_acq_rel);
+          if (phase == 0)
+            while (arrived.load(std::memory_order_acquire) < want) {
+            }
+        }
+      }
+    });
+}
+
+void MgpuPool::shutdown() {
+  if (threads.empty()) return;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    stop.store(true);
+    gen.fetch_add(1, std::memory_order_release);
+  }
+  cv.notify_all();
+  for (auto& t : threads) t.join();
+  threads.clear();
+}
+
+int MgpuPool::run(int n, void* const* d_out, const void* const* d_in) {
+  out_tab = d_out;
+  in_tab = d_in;
+  rc.assign((size_t)n, B200FFT_OK);
+  msg.assign((size_t)n, std::string());
+  arrived.store(0, std::memory_order_release);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    gen.fetch_add(1, std::memory_order_release);
+  }
+  cv.notify_all();
+  while (arrived.load(std::memory_order_acquire) < 2 * n) {
+  }
+  for (int g = 0; g < n; ++g)
+    if (rc[(size_t)g] != B200FFT_OK) return fail(rc[(size_t)g], "device slot %d: %s", g, msg[(size_t)g].c_str());
+  return B200FFT_OK;
+}
+
 int b200fft_mgpu_exec(b200fft_mgpu_plan* m, void* const* d_out, const void* const* d_in) {
   if (!m || !d_out || !d_in) return fail(B200FFT_ERR_INVALID_ARG, "null plan or pointer table");
   const int G = (int)m->slots.size();
   for (int g = 0; g < G; ++g)
     if (!d_out[g] || !d_in[g]) return fail(B200FFT_ERR_INVALID_ARG, "null buffer for device slot %d", g);
-  DevGuard guard;
-  if (m->mode == B200FFT_MGPU_BATCH_SHARD) {
-    for (int g = 0; g < G; ++g) {
-      Slot& s = m->slots[(size_t)g];
-      if (int rc = b200fft_exec(s.plan, d_out[g], d_in[g], s.stream)) return rc;
-    }
-    return B200FFT_OK;
+  int rc = B200FFT_OK;
+  if (m->pool && G > 1) {
+    rc = m->pool->run(G, d_out, d_in);
+  } else {
+    DevGuard guard;
+    for (int phase = 0; phase < 2 && rc == B200FFT_OK; ++phase)
+      for (int g = 0; g < G && rc == B200FFT_OK; ++g) rc = slot_enqueue(m, g, phase, d_out, d_in);
   }
-  // SLAB. A slot may not start scattering call k+1 into a peer's slab while that peer still runs the Z pass of call k.
-  for (int g = 0; g < G; ++g) {
-    Slot& s = m->slots[(size_t)g];
-    B200_CUDA_CHECK(cudaSetDevice(s.device));
-    if (m->executed)
-      for (int h = 0; h < G; ++h)
-        if (h != g) B200_CUDA_CHECK(cudaStreamWaitEvent(s.stream, m->slots[(size_t)h].done, 0));
-    if (int rc = b200fft_exec_scatter(s.plan, d_out, G, g, d_in[g], s.work, s.stream)) return rc;
-    B200_CUDA_CHECK(cudaSetDevice(s.device));
-    B200_CUDA_CHECK(cudaEventRecord(s.scattered, s.stream));
-  }
-  for (int g = 0; g < G; ++g) {
-    Slot& s = m->slots[(size_t)g];
-    B200_CUDA_CHECK(cudaSetDevice(s.device));
-    for (int h = 0; h < G; ++h)
-      if (h != g) B200_CUDA_CHECK(cudaStreamWaitEvent(s.stream, m->slots[(size_t)h].scattered, 0));
-    if (int rc = b200fft_exec(s.planz, d_out[g], d_out[g], s.stream)) return rc;
-    B200_CUDA_CHECK(cudaSetDevice(s.device));
-    B200_CUDA_CHECK(cudaEventRecord(s.done, s.stream));
-  }
-  m->executed = true;
-  return B200FFT_OK;
+  if (rc == B200FFT_OK) m->executed = true;
+  return rc;
 }
 
 int b200fft_mgpu_synchronize(b200fft_mgpu_plan* m) {

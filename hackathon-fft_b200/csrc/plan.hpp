@@ -31,6 +31,7 @@ struct Scatter {
   void* const* peer_out = nullptr;  // HOST array of npeers device pointers (copied into the kernel's arguments)
   int npeers = 0;
   int my_rank = 0;
+  long long zbase = -1;  // first z plane of this call inside the peers' slabs; -1 = my_rank * (planes of this call)
 };
 
 // which buffer a pass reads / writes

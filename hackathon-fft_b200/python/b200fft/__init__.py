@@ -78,6 +78,7 @@ SYMBOLS = [
     ("b200fft_host_register", ctypes.c_int, [_vp, ctypes.c_size_t]),
     ("b200fft_host_unregister", ctypes.c_int, [_vp]),
     ("b200fft_exec_scatter", ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    ("b200fft_exec_scatter_at", ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int64, _vp, _vp, _vp]),
     ("b200fft_malloc", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_size_t]),
     ("b200fft_free", ctypes.c_int, [_vp]),
     ("b200fft_ipc_export", ctypes.c_int, [_vp, ctypes.c_char_p]),

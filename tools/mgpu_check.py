@@ -88,6 +88,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--gpus", type=int, default=0)
     ap.add_argument("--batch-per-gpu", type=int, default=100000)
+    ap.add_argument("--slab-only", action="store_true", help="parity at 256^3 and device-resident timing only")
     args = ap.parse_args()
     G = args.gpus or torch.cuda.device_count()
     devs = list(range(G))
@@ -97,7 +98,10 @@ def main():
     n = args.size
     ms, text = slab_time(n, devs)
     print(json.dumps({"what": "mgpu slab %d^3 device-resident" % n, "gpus": G, "ms": round(ms, 4),
-                      "gflops": round(5.0 * n ** 3 * math.log2(n ** 3) / ms / 1e6, 1), "plan": text.strip().split("\n")[:1]}), flush=True)
+                      "gflops": round(5.0 * n ** 3 * math.log2(n ** 3) / ms / 1e6, 1), "plan": text.strip().split("\n")[:1],
+                      "env": {k: v for k, v in os.environ.items() if k.startswith("B200FFT_")}}), flush=True)
+    if args.slab_only:
+        return
     # host paths
     lay = (1, n, n, n, 2)
     plan = b200fft.MgpuPlan("float32", "float32", lay, lay, devices=devs, mode=b200fft.MGPU_SLAB)
