@@ -192,9 +192,81 @@ struct Dft<4, INV> {
   }
 };
 
+// Primes above this run the symmetric-pair form as LOOPS over a constant table instead of fully unrolled straight-line
+// code: a radix-97 butterfly unrolls to ~9000 FMAs with compile-time coefficients, which NVRTC needs 20 s to schedule
+// (127: 60 s); the looped form compiles in about a second and is only ever built by the plan-time specialisation tier
+// (csrc/jit.cu), where every namespace-scope entity is a device entity (-default-device).
+constexpr int kLoopedPrimeMin = 64;
+constexpr bool looped_prime(int r) {
+#ifdef __CUDACC_RTC__
+  return r > kLoopedPrimeMin && r % 2 == 1 && smallest_factor(r) == r;
+#else
+  return (void)r, false;
+#endif
+}
+
+#ifdef __CUDACC_RTC__
+template <int R>
+struct PrimeTable {
+  float c[R], s[R];  // cos / sin of 2*pi*k/R
+};
+template <int R>
+constexpr PrimeTable<R> make_prime_table() {
+  PrimeTable<R> t{};
+  for (int k = 0; k < R; ++k) {
+    const CxD v = cx_unit(k, R);
+    t.c[k] = float(v.re);
+    t.s[k] = float(v.im);
+  }
+  return t;
+}
+template <int R>
+struct PrimeTw {
+  static constexpr PrimeTable<R> tab = make_prime_table<R>();
+};
+
+template <int R, bool INV>
+struct Dft<R, INV, std::enable_if_t<looped_prime(R)>> {
+  static B200_HD void run(float2 (&x)[R]) {
+    constexpr int H = (R - 1) / 2;
+    float2 a[H], b[H];
+#pragma unroll 4
+    for (int j = 1; j <= H; ++j) {
+      a[j - 1] = cadd(x[j], x[R - j]);
+      b[j - 1] = csub(x[j], x[R - j]);
+    }
+    const float2 x0 = x[0];
+    float2 s0 = x0;
+#pragma unroll 4
+    for (int j = 0; j < H; ++j) s0 = cadd(s0, a[j]);
+    x[0] = s0;
+#pragma unroll 1
+    for (int k = 1; k <= H; ++k) {
+      float2 A = x0, B = make_float2(0.f, 0.f);
+      int idx = 0;  // (j * k) mod R
+#pragma unroll 4
+      for (int j = 1; j <= H; ++j) {
+        idx += k;
+        if (idx >= R) idx -= R;
+        const float c = PrimeTw<R>::tab.c[idx], s = PrimeTw<R>::tab.s[idx];
+        A.x = fmaf(c, a[j - 1].x, A.x);
+        A.y = fmaf(c, a[j - 1].y, A.y);
+        B.x = fmaf(s, b[j - 1].x, B.x);
+        B.y = fmaf(s, b[j - 1].y, B.y);
+      }
+      // forward: X_k = A - iB, X_{R-k} = A + iB ; inverse: swapped
+      const float2 lo = make_float2(A.x + B.y, A.y - B.x);
+      const float2 hi = make_float2(A.x - B.y, A.y + B.x);
+      x[k] = INV ? hi : lo;
+      x[R - k] = INV ? lo : hi;
+    }
+  }
+};
+#endif
+
 // any odd radix that is prime (or that we choose not to split): symmetric-pair form
 template <int R, bool INV>
-struct Dft<R, INV, std::enable_if_t<(R > 2) && (R % 2 == 1) && smallest_factor(R) == R>> {
+struct Dft<R, INV, std::enable_if_t<(R > 2) && (R % 2 == 1) && smallest_factor(R) == R && !looped_prime(R)>> {
   static B200_HD void run(float2 (&x)[R]) {
     constexpr int H = (R - 1) / 2;
     float2 a[H], b[H];

@@ -360,7 +360,7 @@ std::shared_ptr<JitKernel> get_kernel(const JitSpec& spec, int device) {
 // (the longest-processing-time rule rt.cu uses); a prime base above 32 (the reference allows any prime, fft.mojo:83-104
 // lists up to 97) becomes a stage of its own, up to JIT_MAX_PRIME.
 constexpr int JIT_MAX_RADIX = 32;
-constexpr int JIT_MAX_PRIME = 64;
+constexpr int JIT_MAX_PRIME = 127;  // unrolled codelets up to 61, looped ones above (dft.cuh: looped_prime)
 constexpr int JIT_MAX_STAGES = 5;
 
 bool jit_group_cap(const std::vector<uint32_t>& ordered, int cap, std::vector<int>* out, int max_stages = JIT_MAX_STAGES) {

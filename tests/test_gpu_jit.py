@@ -33,6 +33,12 @@ CASES = [
     ((3, 6, 10), None, False, 2),              # tiles wider than the strided axis's inner extent
     ((2, 90, 5), None, False, 2),              # inner extent 5 < 8 columns
     ((300, 210), None, False, 2),
+    # primes above 64: looped codelets over a constant table (dft.cuh: looped_prime) — the reference's prime list goes to 97
+    ((11, 194), [[97, 2]], False, 2),
+    ((5, 67), None, True, 2),
+    ((4, 7, 89 * 3), None, False, 2),
+    ((3, 127), [[127]], False, 2),
+    ((6, 83, 4), None, False, 2),              # a large prime on a strided axis
 ]
 
 
@@ -183,6 +189,7 @@ F64_CASES = [
     ((3, 6, 4, 8), "uint8", 1, False, None),
     ((7, 1000), "float32", 2, False, None),                  # fp32 in, fp64 out
     ((3, 74), "float64", 2, False, None),                    # 37 x 2
+    ((3, 97), "float64", 2, False, None),                    # looped radix-97 codelet in fp64
     ((2, 30, 21), "float64", 1, True, None),
 ]
 

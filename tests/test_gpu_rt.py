@@ -62,7 +62,7 @@ def test_rt_tier(oracle, shape, bases, inverse, in_dtype, comps):
 def test_radix_above_64_stays_generic():
     p = b200fft.plan_fft("float32", "float32", (4, 74, 2), (4, 74, 2), flags=b200fft.FLAG_FORCE_RT)   # 74 = 37 * 2
     assert "generic" in p.describe()                                      # the rt tier's codelets stop at radix 32
-    p = b200fft.plan_fft("float32", "float32", (4, 134, 2), (4, 134, 2))    # 134 = 67 * 2: above the JIT tier's limit too
+    p = b200fft.plan_fft("float32", "float32", (4, 262, 2), (4, 262, 2), bases=[[131, 2]])   # above the specialised tier's 127 too
     assert "generic" in p.describe()
     p = b200fft.plan_fft("float32", "float32", (4, 64, 2), (4, 64, 2), _test="generic")
     assert "generic" in p.describe()

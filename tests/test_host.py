@@ -274,11 +274,12 @@ def test_jit_sources_compile_with_nvrtc_for_sm100a():
                      (dict(n=243, half=1), "rows_r2c_odd_kernel<243, b200fft::Radices<27, 9>"),
                      (dict(n=360, inner=360, inverse=True), "cols_kernel<360, b200fft::Radices<20, 18>, 16, 288, true, false>"),
                      (dict(n=200, real_in=True), "false, true>"),
-                     (dict(n=74), "Radices<37, 2>")):
+                     (dict(n=74), "Radices<37, 2>"),
+                     (dict(n=194, bases=[97, 2]), "Radices<97, 2>")):          # looped prime codelet: compiles in under a second
         rep = b200fft.jit_probe(**kw)
         assert want in rep and "cubin=" in rep, rep
     with pytest.raises(b200fft.B200FFTError) as e:
-        b200fft.jit_probe(n=134)                       # 67 x 2: left to the generic kernel
+        b200fft.jit_probe(n=262, bases=[131, 2])       # a prime above 127: left to the generic kernel
     assert e.value.status == 4
     with pytest.raises(b200fft.B200FFTError) as e:
         b200fft.jit_probe(n=100, bases=[3])
