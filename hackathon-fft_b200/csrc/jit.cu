@@ -9,10 +9,16 @@
 // template arguments, gets a cubin for sm_100a back, loads it with the driver API and launches it like any other pass.
 // One compile per distinct (kind, N, radices, tile, threads, direction, input kind) per device, cached for the life of
 // the process. If libnvrtc cannot be loaded or the compile fails, the axis falls to the runtime-length tier (rt.cu).
+// Compiled kernels are also kept on disk (see disk_cache_dir below), so only the first process ever to plan a shape pays.
 //   B200FFT_JIT=0        disable this tier          B200FFT_JIT_VERBOSE=1   print compile times / logs to stderr
+//   B200FFT_JIT_CACHE=0  no on-disk cache           B200FFT_JIT_CACHE_DIR   where it lives (default ~/.cache/b200fft)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
 
 #include <algorithm>
 #include <chrono>
@@ -289,6 +295,82 @@ int compile(const JitSpec& spec, std::vector<char>* cubin, std::string* lowered,
   return B200FFT_OK;
 }
 
+// ---- on-disk cache of compiled kernels: a new process does not pay NVRTC again for a kernel some earlier process built.
+// One file per kernel, named by a hash of the specialisation key AND of the embedded header text (a rebuilt library never
+// picks up a stale cubin). Directory: $B200FFT_JIT_CACHE_DIR, else $XDG_CACHE_HOME/b200fft, else $HOME/.cache/b200fft;
+// B200FFT_JIT_CACHE=0 turns it off; an unwritable directory is silently not used.
+uint64_t fnv1a(const char* p, size_t n, uint64_t h = 1469598103934665603ull) {
+  for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)p[i]) * 1099511628211ull;
+  return h;
+}
+std::string disk_cache_dir() {
+  if (const char* e = getenv("B200FFT_JIT_CACHE"))
+    if (atoi(e) == 0) return "";
+  std::string dir;
+  if (const char* e = getenv("B200FFT_JIT_CACHE_DIR")) dir = e;
+  else if (const char* x = getenv("XDG_CACHE_HOME")) dir = std::string(x) + "/b200fft";
+  else if (const char* h = getenv("HOME")) dir = std::string(h) + "/.cache/b200fft";
+  if (dir.empty()) return "";
+  std::string partial;
+  for (size_t i = 0; i <= dir.size(); ++i)  // mkdir -p
+    if (i == dir.size() || (dir[i] == '/' && i > 0)) {
+      partial = dir.substr(0, i);
+      if (mkdir(partial.c_str(), 0755) != 0 && errno != EEXIST) return "";
+    }
+  return dir;
+}
+std::string disk_cache_path(const JitSpec& spec) {
+  static const uint64_t src_hash = [] {
+    uint64_t h = fnv1a(k_src_rtc_prelude, strlen(k_src_rtc_prelude));
+    h = fnv1a(k_src_dft, strlen(k_src_dft), h);
+    h = fnv1a(k_src_tma, strlen(k_src_tma), h);
+    return fnv1a(k_src_fast, strlen(k_src_fast), h);
+  }();
+  static const std::string dir = disk_cache_dir();
+  if (dir.empty()) return "";
+  const std::string key = spec.key() + "|" + spec.smem_expression();
+  char name[64];
+  snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)fnv1a(key.data(), key.size(), src_hash));
+  return dir + name;
+}
+// file = "B2FJ" | u32 name length | lowered name | cubin
+bool disk_cache_load(const std::string& path, std::vector<char>* cubin, std::string* lowered) {
+  if (path.empty()) return false;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  char magic[4];
+  uint32_t n = 0;
+  bool ok = fread(magic, 1, 4, f) == 4 && memcmp(magic, "B2FJ", 4) == 0 && fread(&n, 4, 1, f) == 1 && n > 0 && n < 4096;
+  if (ok) {
+    lowered->resize(n);
+    ok = fread(&(*lowered)[0], 1, n, f) == n;
+  }
+  if (ok) {
+    const long at = ftell(f);
+    fseek(f, 0, SEEK_END);
+    const long end = ftell(f);
+    fseek(f, at, SEEK_SET);
+    ok = end > at;
+    if (ok) {
+      cubin->resize((size_t)(end - at));
+      ok = fread(cubin->data(), 1, cubin->size(), f) == cubin->size();
+    }
+  }
+  fclose(f);
+  return ok;
+}
+void disk_cache_store(const std::string& path, const std::vector<char>& cubin, const std::string& lowered) {
+  if (path.empty()) return;
+  const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const uint32_t n = (uint32_t)lowered.size();
+  const bool ok = fwrite("B2FJ", 1, 4, f) == 4 && fwrite(&n, 4, 1, f) == 1 && fwrite(lowered.data(), 1, n, f) == n &&
+                  fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  fclose(f);
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());  // rename: readers never see a partial file
+}
+
 std::mutex g_jit_mutex;
 std::map<std::string, std::shared_ptr<JitKernel>>& cache() {
   static std::map<std::string, std::shared_ptr<JitKernel>> c;  // key = device ordinal + spec key; modules live until exit
@@ -309,10 +391,15 @@ std::shared_ptr<JitKernel> get_kernel(const JitSpec& spec, int device) {
   std::vector<char> cubin;
   std::string lowered, log;
   double ms = 0;
-  if (compile(spec, &cubin, &lowered, &log, &ms) != B200FFT_OK) {
-    if (getenv("B200FFT_JIT_VERBOSE")) fprintf(stderr, "[b200fft jit] %s\n", last_error().c_str());
-    cache()[key] = nullptr;  // do not retry a failing compile on every plan
-    return nullptr;
+  const std::string on_disk = disk_cache_path(spec);
+  const bool from_disk = disk_cache_load(on_disk, &cubin, &lowered);
+  if (!from_disk) {
+    if (compile(spec, &cubin, &lowered, &log, &ms) != B200FFT_OK) {
+      if (getenv("B200FFT_JIT_VERBOSE")) fprintf(stderr, "[b200fft jit] %s\n", last_error().c_str());
+      cache()[key] = nullptr;  // do not retry a failing compile on every plan
+      return nullptr;
+    }
+    disk_cache_store(on_disk, cubin, lowered);
   }
   auto k = std::make_shared<JitKernel>();
   k->cubin_bytes = cubin.size();
@@ -321,6 +408,7 @@ std::shared_ptr<JitKernel> get_kernel(const JitSpec& spec, int device) {
   if (drv.ModuleLoadData(&k->module, cubin.data()) != CUDA_SUCCESS || drv.ModuleGetFunction(&k->fn, k->module, lowered.c_str()) != CUDA_SUCCESS) {
     fail(B200FFT_ERR_CUDA, "cannot load the compiled module for %s", spec.expression().c_str());
     if (k->module) drv.ModuleUnload(k->module);
+    if (from_disk) remove(on_disk.c_str());  // a damaged cache file: the next plan compiles afresh
     cache()[key] = nullptr;
     return nullptr;
   }
@@ -895,11 +983,16 @@ int jit_probe(int64_t n, int64_t inner, const std::vector<uint32_t>& ordered, bo
   std::vector<char> cubin;
   std::string lowered, log;
   double ms = 0;
-  const int rc = compile(spec, &cubin, &lowered, &log, &ms);
-  if (rc != B200FFT_OK) return rc;
-  char buf[640];
-  snprintf(buf, sizeof buf, "%s: %s, smem=%zuB, cubin=%zuB, %.0f ms, symbol %s", spec.name().c_str(), spec.expression().c_str(), spec.smem(),
-           cubin.size(), ms, lowered.c_str());
+  const std::string on_disk = disk_cache_path(spec);
+  const bool from_disk = disk_cache_load(on_disk, &cubin, &lowered);
+  if (!from_disk) {
+    const int rc = compile(spec, &cubin, &lowered, &log, &ms);
+    if (rc != B200FFT_OK) return rc;
+    disk_cache_store(on_disk, cubin, lowered);
+  }
+  char buf[700];
+  snprintf(buf, sizeof buf, "%s: %s, smem=%zuB, cubin=%zuB, %.0f ms%s, symbol %s", spec.name().c_str(), spec.expression().c_str(), spec.smem(),
+           cubin.size(), ms, from_disk ? " (disk cache)" : "", lowered.c_str());
   *report = buf;
   return B200FFT_OK;
 }

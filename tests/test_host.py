@@ -4,6 +4,7 @@ compile-time plan rules (compared with the oracle's independent restatement)."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -284,3 +285,23 @@ def test_jit_sources_compile_with_nvrtc_for_sm100a():
     with pytest.raises(b200fft.B200FFTError) as e:
         b200fft.jit_probe(n=100, bases=[3])
     assert e.value.status == 3
+
+
+def test_jit_disk_cache(tmp_path):
+    """A kernel compiled by one process is loaded from the on-disk cache by the next (fresh processes: the cache
+    directory is read once per process); a rebuilt library (different header text) or another key never matches."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); import b200fft; print(b200fft.jit_probe(n=%%d))"
+            % os.path.join(ROOT, "hackathon-fft_b200", "python"))
+    env = dict(os.environ, B200FFT_JIT_CACHE_DIR=str(tmp_path / "cache"))
+    first = subprocess.run([sys.executable, "-c", code % 1000], env=env, capture_output=True, text=True, check=True).stdout
+    assert "disk cache" not in first and "cubin=" in first
+    files = os.listdir(tmp_path / "cache")
+    assert len(files) == 1 and files[0].endswith(".cubin")
+    second = subprocess.run([sys.executable, "-c", code % 1000], env=env, capture_output=True, text=True, check=True).stdout
+    assert "(disk cache)" in second and second.split("symbol ")[1] == first.split("symbol ")[1]
+    other = subprocess.run([sys.executable, "-c", code % 100], env=env, capture_output=True, text=True, check=True).stdout
+    assert "disk cache" not in other and len(os.listdir(tmp_path / "cache")) == 2
+    off = subprocess.run([sys.executable, "-c", code % 1000], env=dict(env, B200FFT_JIT_CACHE="0"), capture_output=True, text=True,
+                         check=True).stdout
+    assert "disk cache" not in off

@@ -65,6 +65,7 @@ def jit_listings():
     out = []
     with tempfile.TemporaryDirectory() as tmp:
         os.environ["B200FFT_JIT_DUMP_DIR"] = tmp
+        os.environ["B200FFT_JIT_CACHE"] = "0"   # compile, do not load an earlier process's cubin
         for fname, kw in JIT_KERNELS:
             before = set(os.listdir(tmp))
             rep = b200fft.jit_probe(**kw)
