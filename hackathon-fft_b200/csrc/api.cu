@@ -169,8 +169,12 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
     }
     return B200FFT_OK;
   }
+  // the two innermost axes in one tile per (y, x) plane when a plane kernel covers them (plane_registry.cu): the outer
+  // axes' strided passes first (input -> workspace), then the plane pass (-> output)
+  std::unique_ptr<Pass> plane = dry ? nullptr : make_plane_c2r_pass(*plan);
+  const int first_cols_axis = plane ? last - 2 : last - 1;
   bool any = false;
-  for (int axis = last - 1; axis >= 0; --axis) {
+  for (int axis = first_cols_axis; axis >= 0; --axis) {
     if (!p.axes[axis].transformed) continue;
     int rc = add(axis, half_view(axis), any ? work_spec : in_spec, HALF_NONE, any ? BUF_WORK : BUF_INPUT, BUF_WORK);
     if (rc) return rc;
@@ -183,6 +187,13 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
       cudaGetLastError();
       return fail(B200FFT_ERR_ALLOC, "cannot allocate %zu B of C2R workspace", plan->workspace_bytes);
     }
+  }
+  if (plane) {
+    plane->src_sel = any ? BUF_WORK : BUF_INPUT;
+    plane->dst_sel = BUF_OUTPUT;
+    plane->axis = last;
+    plan->passes.push_back(std::move(plane));
+    return B200FFT_OK;
   }
   return add(last, rows, any ? work_spec : in_spec, HALF_C2R, any ? BUF_WORK : BUF_INPUT, BUF_OUTPUT);
 }

@@ -175,3 +175,37 @@ def test_odd_c2r_on_the_compile_time_kernel():
         got = out.cpu().numpy()[..., 0].astype(np.float64)
         assert np.linalg.norm(got - real) <= 2e-6 * np.sqrt(len(axes)) * np.linalg.norm(real), desc
         plan.destroy()
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 64, 64), (3, 128, 128, 128), (9, 64, 64), (2, 3, 5, 64, 64), (1, 6, 128, 128)])
+def test_plane_c2r_kernel(shape, monkeypatch):
+    """Half-spectrum inverse: the two innermost axes in ONE tile per (y, x) plane (csrc/plane.cuh) instead of a strided pass
+    over the ragged n/2+1 extent + a row pass. Against numpy irfftn, and against the per-axis plan of the same library."""
+    import torch
+    if shape[-1] == 128:
+        monkeypatch.setenv("B200FFT_PLANE_C2R", "1")   # the 128 x 128 variant is opt-in (one CTA per SM: slower than per axis)
+    rng = np.random.default_rng(12)
+    axes = tuple(range(1, len(shape)))
+    real = rng.standard_normal(shape)
+    spec = np.fft.rfftn(real, axes=axes)
+    x = torch.from_numpy(np.stack([spec.real, spec.imag], axis=-1).astype(np.float32)).cuda()
+    keep = x.clone()
+    plan = b200fft.plan_fft("float32", "float32", tuple(x.shape), shape + (1,), real_mode=b200fft.REAL_HALF, inverse=True)
+    desc = plan.describe()
+    assert "c2rplane%dx%d" % (shape[-2], shape[-1]) in desc, desc
+    assert plan.launches == len(shape) - 2          # one pass per outer axis + the plane pass
+    out = torch.full(shape + (1,), float("nan"), device="cuda")
+    b200fft.fft(out, x, plan=plan)
+    torch.cuda.synchronize()
+    assert torch.equal(x, keep)                      # the half spectrum is not overwritten
+    got = out.cpu().numpy()[..., 0].astype(np.float64)
+    assert np.linalg.norm(got - real) <= 2e-6 * np.sqrt(len(axes)) * np.linalg.norm(real), desc
+    monkeypatch.setenv("B200FFT_PLANE_C2R", "0")
+    plain = b200fft.plan_fft("float32", "float32", tuple(x.shape), shape + (1,), real_mode=b200fft.REAL_HALF, inverse=True)
+    assert "c2rplane" not in plain.describe()
+    out2 = torch.empty_like(out)
+    b200fft.fft(out2, x, plan=plain)
+    torch.cuda.synchronize()
+    assert float((out - out2).norm() / out2.norm()) < 1e-6
+    plan.destroy()
+    plain.destroy()
