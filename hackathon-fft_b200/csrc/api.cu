@@ -124,7 +124,10 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
 
   // one persistent kernel for all axes when a fused variant covers the problem (fused_registry.cu); the per-axis
   // passes are still built and kept behind it as its fallback (a refused cooperative launch)
-  if (!dry && !plan->building_fallback) {
+  // B200FFT_PLANE=1: prefer the two-pass plane plan (plane_registry.cu) over the fused persistent kernel wherever both exist
+  bool plane_first = false;
+  if (const char* e = getenv("B200FFT_PLANE")) plane_first = atoi(e) != 0;
+  if (!dry && !plan->building_fallback && !plane_first) {
     std::unique_ptr<Pass> fused = make_fused_pass(*plan);
     if (fused) {
       plan->building_fallback = true;
@@ -133,6 +136,29 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
       if (rc == B200FFT_OK) fused->fallback = std::move(plan->passes);
       plan->passes.clear();
       plan->passes.push_back(std::move(fused));
+      return B200FFT_OK;
+    }
+  }
+
+  // forward half spectrum / complex / real input: the two innermost axes as ONE plane pass where a plane kernel covers them
+  if (!dry && !(p.half && p.desc.inverse)) {
+    std::unique_ptr<Pass> plane = make_plane_fwd_pass(*plan);
+    if (plane) {
+      plane->src_sel = BUF_INPUT;
+      plane->dst_sel = BUF_OUTPUT;
+      plane->axis = last;
+      plan->passes.push_back(std::move(plane));
+      const int64_t hb2 = p.axes[last].n / 2 + 1;
+      for (int axis = last - 2; axis >= 0; --axis) {
+        if (!p.axes[axis].transformed) continue;
+        AxisView v = view_of(p, axis);
+        if (p.half) {  // strided passes see the last axis as n/2+1 bins
+          v.inner = hb2;
+          for (int a = axis + 1; a < last; ++a) v.inner *= p.axes[a].n;
+        }
+        int rc = add(axis, v, work_spec, HALF_NONE, BUF_OUTPUT, BUF_OUTPUT);
+        if (rc) return rc;
+      }
       return B200FFT_OK;
     }
   }

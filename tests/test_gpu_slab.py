@@ -18,7 +18,8 @@ def test_exec_scatter_virtual_ranks(dims, G):
     g = torch.Generator(device="cuda").manual_seed(3)
     full = torch.randn((Z, Y, X, 2), generator=g, device="cuda")
     recv = [torch.full((Z, yl, X, 2), float("nan"), device="cuda") for _ in range(G)]
-    plan2d = b200fft.plan_fft("float32", "float32", (zl, Y, X, 2), (zl, Y, X, 2))
+    plan2d = b200fft.plan_fft("float32", "float32", (zl, Y, X, 2), (zl, Y, X, 2),
+                              flags=b200fft.FLAG_NO_FUSED)      # exec_scatter drives per-axis passes (include/b200fft.h)
     planz = b200fft.plan_fft("float32", "float32", (1, Z, yl, X, 2), (1, Z, yl, X, 2), axis_mask=1)
     work = torch.empty((zl, Y, X, 2), device="cuda")
     st = torch.cuda.current_stream().cuda_stream
