@@ -112,6 +112,21 @@ struct C2CPlaneV {
     return e;
   }
 };
+template <int NY, int NX, class RLY, class RLX, int NT>
+struct C2CPlaneIpV {
+  static void launch(bool inv, bool real, const PlaneFwdArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    if (inv) c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, true, false><<<grid, NT, smem, st>>>(a);
+    else if (real) c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, false, true><<<grid, NT, smem, st>>>(a);
+    else c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, false, false><<<grid, NT, smem, st>>>(a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, true, false>, attr, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, false, true>, attr, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, false, false>, attr, (int)smem);
+    return e;
+  }
+};
 template <int NY, int H, class RLY, class RLX, int NT>
 struct R2CPlaneV {
   static void launch(bool, bool, const PlaneFwdArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
@@ -135,6 +150,18 @@ PlaneFwdVariant c2c64_variant() {
   return c;
 }
 template <int NT>
+PlaneFwdVariant c2c64_ip_variant() {
+  using RY = Radices<8, 8>;
+  using RX = Radices<8, 8>;
+  PlaneFwdVariant c;
+  c.r2c = false; c.ny = 64; c.nx = 64; c.ry = radix_vec<RY>(); c.rx = radix_vec<RX>(); c.threads = NT;
+  c.smem = c2c_plane_ip_smem_bytes<64, 64>();
+  c.launch = &C2CPlaneIpV<64, 64, RY, RX, NT>::launch;
+  c.prepare = &C2CPlaneIpV<64, 64, RY, RX, NT>::prepare;
+  c.name = "plane64x64(8x8;8x8)_inplace_t" + std::to_string(NT);
+  return c;
+}
+template <int NT>
 PlaneFwdVariant r2c64_variant() {
   using RY = Radices<8, 8>;
   using RX = Radices<8, 4>;
@@ -154,6 +181,10 @@ const std::vector<PlaneFwdVariant>& plane_fwd_registry() {
     v.push_back(c2c64_variant<256>());  // 6400 x 64 x 64 C2C: t256 0.0904, t512 0.0986, t128 0.1129 ms (per-axis: 0.1188)
     v.push_back(c2c64_variant<128>());
     v.push_back(c2c64_variant<512>());
+    // one shared-memory buffer, stages exchanged in place through registers (37 KB, 4-6 CTAs per SM): 0.0945 / 0.0984 ms —
+    // occupancy was not the limit: ncu shows the LSU data pipe 81 % busy in the two-buffer kernel, 85 % here (r2_plane.md)
+    v.push_back(c2c64_ip_variant<256>());
+    v.push_back(c2c64_ip_variant<512>());
     v.push_back(r2c64_variant<256>());  // 6400 x 64 x 64 R2C: t256 0.0618, t128 0.0647, t64 0.0712 ms
     v.push_back(r2c64_variant<128>());
     v.push_back(r2c64_variant<64>());
