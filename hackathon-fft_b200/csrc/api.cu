@@ -122,12 +122,21 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
     return B200FFT_OK;
   };
 
-  // one persistent kernel for all axes when a fused variant covers the problem (fused_registry.cu); the per-axis
-  // passes are still built and kept behind it as its fallback (a refused cooperative launch)
-  // B200FFT_PLANE=1: prefer the two-pass plane plan (plane_registry.cu) over the fused persistent kernel wherever both exist
-  bool plane_first = false;
-  if (const char* e = getenv("B200FFT_PLANE")) plane_first = atoi(e) != 0;
-  if (!dry && !plan->building_fallback && !plane_first) {
+  // Forward half spectrum / complex / real input: the two innermost axes as ONE plane pass where a plane kernel covers them
+  // (plane_registry.cu), strided passes for the outer axes. It ties the fused persistent kernel on 100 x 64^3 (0.147 vs
+  // 0.149 ms C2C, 0.090 vs 0.092 ms R2C; profiles/r2_plane.md) with two plain launches — no cooperative grid, no
+  // dependency spinning — so it goes first; B200FFT_FUSED=1, B200FFT_FUSED_PREFER, the PREFER_FUSED flag or B200FFT_PLANE=0
+  // put the fused kernel back in front.
+  std::unique_ptr<Pass> plane;
+  if (!dry && !(p.half && p.desc.inverse)) {
+    bool fused_wanted = (p.desc.flags & B200FFT_FLAG_PREFER_FUSED) != 0 || getenv("B200FFT_FUSED_PREFER") != nullptr;
+    if (const char* e = getenv("B200FFT_FUSED")) fused_wanted = fused_wanted || atoi(e) != 0;
+    if (!fused_wanted || plan->building_fallback) plane = make_plane_fwd_pass(*plan);
+  }
+
+  // one persistent kernel for all axes when a fused variant covers the problem (fused_registry.cu); the other passes
+  // are still built and kept behind it as its fallback (a refused cooperative launch)
+  if (!dry && !plan->building_fallback && !plane) {
     std::unique_ptr<Pass> fused = make_fused_pass(*plan);
     if (fused) {
       plan->building_fallback = true;
@@ -140,27 +149,23 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
     }
   }
 
-  // forward half spectrum / complex / real input: the two innermost axes as ONE plane pass where a plane kernel covers them
-  if (!dry && !(p.half && p.desc.inverse)) {
-    std::unique_ptr<Pass> plane = make_plane_fwd_pass(*plan);
-    if (plane) {
-      plane->src_sel = BUF_INPUT;
-      plane->dst_sel = BUF_OUTPUT;
-      plane->axis = last;
-      plan->passes.push_back(std::move(plane));
-      const int64_t hb2 = p.axes[last].n / 2 + 1;
-      for (int axis = last - 2; axis >= 0; --axis) {
-        if (!p.axes[axis].transformed) continue;
-        AxisView v = view_of(p, axis);
-        if (p.half) {  // strided passes see the last axis as n/2+1 bins
-          v.inner = hb2;
-          for (int a = axis + 1; a < last; ++a) v.inner *= p.axes[a].n;
-        }
-        int rc = add(axis, v, work_spec, HALF_NONE, BUF_OUTPUT, BUF_OUTPUT);
-        if (rc) return rc;
+  if (plane) {
+    plane->src_sel = BUF_INPUT;
+    plane->dst_sel = BUF_OUTPUT;
+    plane->axis = last;
+    plan->passes.push_back(std::move(plane));
+    const int64_t hb2 = p.axes[last].n / 2 + 1;
+    for (int axis = last - 2; axis >= 0; --axis) {
+      if (!p.axes[axis].transformed) continue;
+      AxisView v = view_of(p, axis);
+      if (p.half) {  // strided passes see the last axis as n/2+1 bins
+        v.inner = hb2;
+        for (int a = axis + 1; a < last; ++a) v.inner *= p.axes[a].n;
       }
-      return B200FFT_OK;
+      int rc = add(axis, v, work_spec, HALF_NONE, BUF_OUTPUT, BUF_OUTPUT);
+      if (rc) return rc;
     }
+    return B200FFT_OK;
   }
 
   if (!p.half) {
@@ -197,8 +202,8 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
   }
   // the two innermost axes in one tile per (y, x) plane when a plane kernel covers them (plane_registry.cu): the outer
   // axes' strided passes first (input -> workspace), then the plane pass (-> output)
-  std::unique_ptr<Pass> plane = dry ? nullptr : make_plane_c2r_pass(*plan);
-  const int first_cols_axis = plane ? last - 2 : last - 1;
+  std::unique_ptr<Pass> plane_inv = dry ? nullptr : make_plane_c2r_pass(*plan);
+  const int first_cols_axis = plane_inv ? last - 2 : last - 1;
   bool any = false;
   for (int axis = first_cols_axis; axis >= 0; --axis) {
     if (!p.axes[axis].transformed) continue;
@@ -214,11 +219,11 @@ int build_passes(b200fft_plan* plan, bool dry, std::string* text) {
       return fail(B200FFT_ERR_ALLOC, "cannot allocate %zu B of C2R workspace", plan->workspace_bytes);
     }
   }
-  if (plane) {
-    plane->src_sel = any ? BUF_WORK : BUF_INPUT;
-    plane->dst_sel = BUF_OUTPUT;
-    plane->axis = last;
-    plan->passes.push_back(std::move(plane));
+  if (plane_inv) {
+    plane_inv->src_sel = any ? BUF_WORK : BUF_INPUT;
+    plane_inv->dst_sel = BUF_OUTPUT;
+    plane_inv->axis = last;
+    plan->passes.push_back(std::move(plane_inv));
     return B200FFT_OK;
   }
   return add(last, rows, any ? work_spec : in_spec, HALF_C2R, any ? BUF_WORK : BUF_INPUT, BUF_OUTPUT);

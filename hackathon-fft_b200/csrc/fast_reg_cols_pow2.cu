@@ -4,6 +4,9 @@
 namespace b200fft {
 void register_cols_pow2() {
   reg_cols<64, 16, 128, true, 8, 8>();
+  reg_cols<64, 32, 256, true, 8, 8>();   // wider tiles for the z pass behind a plane pass (B200FFT_PREFER=cols64_8x8_w32 / _w64)
+  reg_cols<64, 64, 512, true, 8, 8>();
+  reg_cols<64, 32, 128, true, 8, 8>();
   reg_cols<128, 16, 128, true, 16, 8>();
   reg_cols<256, 16, 256, true, 16, 16>();
   reg_cols<512, 16, 256, true, 32, 16>();

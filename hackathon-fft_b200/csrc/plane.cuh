@@ -91,6 +91,18 @@ struct PlaneFwdArgs {
   int do_scale;
 };
 
+// the x result handed to the y pass: dense rows with a pitch of NX + 8. With a pitch of NX the four rows a warp writes in
+// the last x stage (lanes = 8 butterflies x 4 rows) start on the same bank: 2 excess wavefronts per store, a quarter of
+// all STS wavefronts of the tile (ncu source page); a pitch = 8 (mod 16) complex puts them on disjoint halves of a wavefront.
+template <int NX>
+struct PlanePadRows {  // (o = y, i = x)
+  static __device__ __forceinline__ int off(int o, int i, int) { return o * (NX + 8) + i; }
+};
+template <int NX>
+struct PlanePadCols {  // the same buffer for the y stages: (i = y, c = x)
+  static __device__ __forceinline__ int off(int, int i, int c) { return i * (NX + 8) + c; }
+};
+
 template <int NY, int NX, class RLY, class RLX>
 constexpr int c2c_plane_exchange_elems() {
   constexpr int ex = max_exchange_elems<RLX, NY, RowLayoutN<NX>::template type>();
@@ -98,7 +110,7 @@ constexpr int c2c_plane_exchange_elems() {
 }
 template <int NY, int NX, class RLY, class RLX>
 constexpr size_t c2c_plane_smem_bytes() {
-  return sizeof(float2) * (size_t)(NY * NX + c2c_plane_exchange_elems<NY, NX, RLY, RLX>());
+  return sizeof(float2) * (size_t)(NY * (NX + 8) + c2c_plane_exchange_elems<NY, NX, RLY, RLX>());
 }
 
 // One Stockham stage whose source and destination are the SAME shared-memory buffer: every butterfly of the tile is read
@@ -193,18 +205,18 @@ __global__ void __launch_bounds__(NT) c2c_plane_kernel(const __grid_constant__ P
   static_assert(RLY::count == 2 && RLX::count == 2, "plane tiles: two super-stages per axis");
   static_assert(RLY::product() == NY && RLX::product() == NX, "radices must multiply to the axis lengths");
   extern __shared__ __align__(16) float2 smem_f2[];
-  float2* S = smem_f2;             // x result, dense [y][x]
-  float2* R1 = smem_f2 + NY * NX;  // exchange
+  float2* S = smem_f2;                   // x result, rows of pitch NX + 8
+  float2* R1 = smem_f2 + NY * (NX + 8);  // exchange
   const long long p = blockIdx.x;
   const void* in = REAL ? (const void*)(reinterpret_cast<const in_scalar*>(a.in) + p * (long long)(NY * NX))
                         : (const void*)(reinterpret_cast<const in_vec2*>(a.in) + p * (long long)(NY * NX));
   using LX = typename RowLayoutN<NX>::template type<RLX::r[0], 1>;
   run_stage<RLX::r[0], 1, NX, NY, 1, NT, INV>(GlobalSrc<REAL>{in, NX, 1, NY, 1}, SmemDst<LX>{R1}, a.twx, 1.f, false);
   __syncthreads();
-  run_stage<RLX::r[1], RLX::r[0], NX, NY, 1, NT, INV>(SmemSrc<LX>{R1}, SmemDst<PlaneLayout<NX>>{S}, a.twx + RLX::tw_offset(1), 1.f, false);
+  run_stage<RLX::r[1], RLX::r[0], NX, NY, 1, NT, INV>(SmemSrc<LX>{R1}, SmemDst<PlanePadRows<NX>>{S}, a.twx + RLX::tw_offset(1), 1.f, false);
   __syncthreads();
   using LY = DenseLayout<NY, NX>;
-  run_stage<RLY::r[0], 1, NY, 1, NX, NT, INV>(SmemSrc<LY>{S}, SmemDst<LY>{R1}, a.twy, 1.f, false);
+  run_stage<RLY::r[0], 1, NY, 1, NX, NT, INV>(SmemSrc<PlanePadCols<NX>>{S}, SmemDst<LY>{R1}, a.twy, 1.f, false);
   __syncthreads();
   GlobalDst dst{a.out + p * (long long)(NY * NX), 0, NX, 1, NX};
   run_stage<RLY::r[1], RLY::r[0], NY, 1, NX, NT, INV>(SmemSrc<LY>{R1}, dst, a.twy + RLY::tw_offset(1), a.scale, a.do_scale != 0);

@@ -11,6 +11,14 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True)
+def _fused_before_plane(monkeypatch):
+    """Since round 2 the two-pass plane plan (csrc/plane.cuh, tests/test_gpu_plane.py) is tried before the fused persistent
+    kernel where both cover a problem (they tie on 100 x 64^3). These tests are about the fused kernels: switch the plane
+    passes off, which is also what a user who wants the fused kernel everywhere does."""
+    monkeypatch.setenv("B200FFT_PLANE", "0")
+
+
+@pytest.fixture(autouse=True)
 def _enable_fused(monkeypatch):
     monkeypatch.setenv("B200FFT_FUSED", "1")   # opt-in while the per-axis kernels are faster
 
@@ -189,7 +197,7 @@ def test_refused_cooperative_launch_falls_back_to_per_axis_passes(monkeypatch):
     out = torch.full_like(x, float("nan"))
     b200fft.fft(out, x, plan=plan)
     torch.cuda.synchronize()
-    assert b200fft.launch_count() - before == 2          # the fallback plan (plane pass + strided z pass), not one fused launch
+    assert b200fft.launch_count() - before == 3          # three per-axis kernels (plane passes are off here), not one fused launch
     _check(out, _ref(x))
     assert float((out - good).norm() / good.norm()) < 1e-6
     monkeypatch.delenv("B200FFT_TEST_REFUSE_COOP")
