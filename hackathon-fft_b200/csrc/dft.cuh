@@ -267,6 +267,7 @@ struct Dft<R, INV, std::enable_if_t<looped_prime(R)>> {
 // any odd radix that is prime (or that we choose not to split): symmetric-pair form
 template <int R, bool INV>
 struct Dft<R, INV, std::enable_if_t<(R > 2) && (R % 2 == 1) && smallest_factor(R) == R && !looped_prime(R)>> {
+  static constexpr bool real_form = true;
   static B200_HD void run(float2 (&x)[R]) {
     constexpr int H = (R - 1) / 2;
     float2 a[H], b[H];
@@ -299,7 +300,42 @@ struct Dft<R, INV, std::enable_if_t<(R > 2) && (R % 2 == 1) && smallest_factor(R
       x[R - k] = INV ? lo : hi;
     });
   }
+  // The same butterfly on REAL inputs (every x[j].y == 0: stage 0 of a real-input transform): the pair sums a_j and
+  // differences b_j are real, so each output pair costs 2 FMAs per j instead of 4 and X_{R-k} = conj X_k.
+  static B200_HD void run_real(float2 (&x)[R]) {
+    constexpr int H = (R - 1) / 2;
+    float a[H], b[H];
+    static_for<H>([&](auto jc) {
+      constexpr int j = decltype(jc)::value + 1;
+      a[j - 1] = x[j].x + x[R - j].x;
+      b[j - 1] = x[j].x - x[R - j].x;
+    });
+    const float x0 = x[0].x;
+    float s0 = x0;
+    static_for<H>([&](auto jc) { s0 += a[decltype(jc)::value]; });
+    x[0] = make_float2(s0, 0.f);
+    static_for<H>([&](auto kc) {
+      constexpr int k = decltype(kc)::value + 1;
+      float A = x0, B = 0.f;
+      static_for<H>([&](auto jc) {
+        constexpr int j = decltype(jc)::value + 1;
+        constexpr float c = Tw<(j * k) % R, R, true>::re;
+        constexpr float s = Tw<(j * k) % R, R, true>::im;
+        A = fmaf(c, a[j - 1], A);
+        B = fmaf(s, b[j - 1], B);
+      });
+      // forward: X_k = A - iB, X_{R-k} = A + iB ; inverse: swapped
+      x[k] = make_float2(A, INV ? B : -B);
+      x[R - k] = make_float2(A, INV ? -B : B);
+    });
+  }
 };
+
+// run_real where a codelet has one (the unrolled odd primes), the general butterfly otherwise
+template <class D, class = void>
+struct has_run_real : std::false_type {};
+template <class D>
+struct has_run_real<D, std::enable_if_t<D::real_form>> : std::true_type {};
 
 // composite radix: Cooley-Tukey on registers, R = R1 * R2, n = R2*n1 + n2, k = k1 + R1*k2
 template <int R, bool INV>

@@ -145,6 +145,12 @@ struct is_whole : std::false_type {};
 template <class T>
 struct is_whole<T, std::enable_if_t<T::whole>> : std::true_type {};
 
+// sources whose imaginary parts are all zero (real input arrays): stage 0 may use a codelet's real-input form
+template <class T>
+struct is_real_src : std::false_type {};
+template <bool COHERENT>
+struct is_real_src<GlobalSrc<true, COHERENT>> : std::true_type {};
+
 template <class Layout>
 struct SmemSrc {
   const float2* buf;
@@ -224,7 +230,8 @@ __device__ __forceinline__ void run_stage(const Src& src, const Dst& dst, const 
 #pragma unroll
         for (int j = 1; j < R; ++j) x[j] = cmulf(x[j], tw_load<TWS>(tw, (j - 1) * P + p));
       }
-      Dft<R, INV>::run(x);
+      if constexpr (P == 1 && is_real_src<Src>::value && has_run_real<Dft<R, INV>>::value) Dft<R, INV>::run_real(x);
+      else Dft<R, INV>::run(x);
       if (do_scale) {
 #pragma unroll
         for (int k = 0; k < R; ++k) { x[k].x *= scale; x[k].y *= scale; }
