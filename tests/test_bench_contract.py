@@ -41,3 +41,20 @@ def test_gpu_arm_refuses_to_run_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_shape_rows_find_their_plan_traffic():
+    """bench.py's shapes[] rows report DRAM traffic / algorithmic bytes from profiles/traffic.json "plan:<row name>" entries
+    (ncu captures of one exec of the whole plan): every multi-pass BASELINE row must have one, with the kernels of the plan
+    the planner picks today."""
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic = bench._plan_traffic()
+    names = {n for n, _, _ in bench.SHAPES}
+    for row in ("2d_100x640x480", "2d_100x640x480_r2c_half", "3d_100x64x64x64", "3d_100x64x64x64_r2c_half", "3d_10x128x128x128",
+                "3d_1x256x256x256", "3d_1x512x512x512"):
+        assert row in names
+        e = traffic["plan:" + row]
+        assert e["dram_bytes_per_exec"] > 0.9 * e["algorithmic_bytes_per_exec"] and e["launches"] == len(e["kernels"]) >= 1
+    assert "plane_kernel" in traffic["plan:3d_100x64x64x64"]["kernels"][0]          # the default plan, not the fused kernel's capture
+    assert "nd_async_kernel" in traffic["fused-plan:3d_100x64x64x64"]["kernels"][0]

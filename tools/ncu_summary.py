@@ -82,8 +82,9 @@ def main():
         for d in read_report(path):
             tr = d.get("dram_read", 0) + d.get("dram_write", 0)
             ratio = "%.3f" % (tr / float(alg)) if alg else "-"
-            traffic[name] = {"dram_bytes_per_launch": tr, "algorithmic_bytes_per_launch": float(alg) if alg else None,
-                             "kernel": d["kernel"].strip(), "source": os.path.basename(path)}
+            if not name.startswith("plan:"):  # (a plan entry holds the sum over its launches, written above)
+                traffic[name] = {"dram_bytes_per_launch": tr, "algorithmic_bytes_per_launch": float(alg) if alg else None,
+                                 "kernel": d["kernel"].strip(), "source": os.path.basename(path)}
             k = d["kernel"].strip().replace("|", "/")
             lines.append("| %s | `%s` | %.1f | %.1f | %.1f | %s | %.0f | %.1f | %.1f | %d | %d, %d | %d x %d | %d | %.3g |" % (
                 name, k, d.get("time", 0) * 1e6, d.get("dram_read", 0) / 1e6, d.get("dram_write", 0) / 1e6, ratio,
