@@ -38,6 +38,7 @@ for p in (ROOT, os.path.join(ROOT, "hackathon-fft_b200", "python")):
         sys.path.insert(0, p)
 
 import numpy as np
+os.environ.setdefault("B200FFT_JIT_CACHE", "0")  # no on-disk kernel cache outside the repository from this script
 
 METRIC = "batched C2C FFT ms, GFLOP/s & HBM GB/s vs peak at 1/2/4/8 B200 vs cuFFT"
 PRIMARY = {"name": "1D C2C fp32 100000x1024", "shape": (100000, 1024)}

@@ -11,6 +11,11 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 
+# The run-time compiled kernels are cached on disk under ~/.cache/b200fft by default (csrc/jit.cu). The test suite must not
+# write outside the repository: no disk cache here (tests/test_host.py::test_jit_disk_cache points it at a tmp_path).
+os.environ.setdefault("B200FFT_JIT_CACHE", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 

@@ -293,7 +293,7 @@ def test_jit_disk_cache(tmp_path):
     import subprocess
     code = ("import sys; sys.path.insert(0, %r); import b200fft; print(b200fft.jit_probe(n=%%d))"
             % os.path.join(ROOT, "hackathon-fft_b200", "python"))
-    env = dict(os.environ, B200FFT_JIT_CACHE_DIR=str(tmp_path / "cache"))
+    env = dict(os.environ, B200FFT_JIT_CACHE="1", B200FFT_JIT_CACHE_DIR=str(tmp_path / "cache"))
     first = subprocess.run([sys.executable, "-c", code % 1000], env=env, capture_output=True, text=True, check=True).stdout
     assert "disk cache" not in first and "cubin=" in first
     files = os.listdir(tmp_path / "cache")
