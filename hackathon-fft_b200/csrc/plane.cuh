@@ -159,22 +159,22 @@ __device__ __forceinline__ void run_stage_inplace(const Src& src, const Dst& dst
   }
 }
 
-// rows of NI points, one pad element after every 8 (the RowLayout padding of a radix-8 first stage: the scatter of
-// butterfly n to 8 n + k lands on 9 n + k, distinct banks), pitch NI + NI / 8
-template <int NI, int PAD>
+// rows of NI points, one pad element after every Q = first x radix (the RowLayout padding of the first stage: the scatter
+// of butterfly n to Q n + k lands on (Q + 1) n + k, distinct banks), pitch NI + NI / Q
+template <int NI, int Q>
 struct PitchLayout {
-  static constexpr int pitch = NI + PAD;
-  static __device__ __forceinline__ int off(int o, int i, int) { return o * pitch + i + (i >> 3); }
+  static constexpr int pitch = NI + NI / Q;
+  static __device__ __forceinline__ int off(int o, int i, int) { return o * pitch + i + i / Q; }
 };
 // the same buffer seen by the y stages: element (i = y, c = x)
-template <int NI, int PAD>
+template <int NI, int Q>
 struct PitchColsLayout {
-  static __device__ __forceinline__ int off(int, int i, int c) { return i * (NI + PAD) + c + (c >> 3); }
+  static __device__ __forceinline__ int off(int, int i, int c) { return i * (NI + NI / Q) + c + c / Q; }
 };
 
-template <int NY, int NX>
+template <int NY, int NX, class RLX>
 constexpr size_t c2c_plane_ip_smem_bytes() {
-  return sizeof(float2) * (size_t)NY * (NX + 8);
+  return sizeof(float2) * (size_t)NY * (NX + NX / RLX::r[0]);
 }
 
 // In-place variant of c2c_plane_kernel: ONE buffer. x stage 0 global -> B, x stage 1 in place, y stage 0 in place, y stage 1
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(NT) c2c_plane_ip_kernel(const __grid_constant_
   const long long p = blockIdx.x;
   const void* in = REAL ? (const void*)(reinterpret_cast<const in_scalar*>(a.in) + p * (long long)(NY * NX))
                         : (const void*)(reinterpret_cast<const in_vec2*>(a.in) + p * (long long)(NY * NX));
-  using LR = PitchLayout<NX, 8>;
-  using LC = PitchColsLayout<NX, 8>;
+  using LR = PitchLayout<NX, RLX::r[0]>;
+  using LC = PitchColsLayout<NX, RLX::r[0]>;
   run_stage<RLX::r[0], 1, NX, NY, 1, NT, INV>(GlobalSrc<REAL>{in, NX, 1, NY, 1}, SmemDst<LR>{B}, a.twx, 1.f, false);
   __syncthreads();
   run_stage_inplace<RLX::r[1], RLX::r[0], NX, NY, 1, NT, INV>(SmemSrc<LR>{B}, SmemDst<LR>{B}, a.twx + RLX::tw_offset(1));

@@ -155,10 +155,23 @@ PlaneFwdVariant c2c64_ip_variant() {
   using RX = Radices<8, 8>;
   PlaneFwdVariant c;
   c.r2c = false; c.ny = 64; c.nx = 64; c.ry = radix_vec<RY>(); c.rx = radix_vec<RX>(); c.threads = NT;
-  c.smem = c2c_plane_ip_smem_bytes<64, 64>();
+  c.smem = c2c_plane_ip_smem_bytes<64, 64, RX>();
   c.launch = &C2CPlaneIpV<64, 64, RY, RX, NT>::launch;
   c.prepare = &C2CPlaneIpV<64, 64, RY, RX, NT>::prepare;
   c.name = "plane64x64(8x8;8x8)_inplace_t" + std::to_string(NT);
+  return c;
+}
+// 128 x 128 planes only fit as ONE shared buffer (139 KB, one CTA per SM): stages exchanged in place through registers
+template <int NT>
+PlaneFwdVariant c2c128_ip_variant() {
+  using RY = Radices<16, 8>;
+  using RX = Radices<16, 8>;
+  PlaneFwdVariant c;
+  c.r2c = false; c.ny = 128; c.nx = 128; c.ry = radix_vec<RY>(); c.rx = radix_vec<RX>(); c.threads = NT;
+  c.smem = c2c_plane_ip_smem_bytes<128, 128, RX>();
+  c.launch = &C2CPlaneIpV<128, 128, RY, RX, NT>::launch;
+  c.prepare = &C2CPlaneIpV<128, 128, RY, RX, NT>::prepare;
+  c.name = "plane128x128(16x8;16x8)_inplace_t" + std::to_string(NT);
   return c;
 }
 template <int NT>
@@ -185,6 +198,8 @@ const std::vector<PlaneFwdVariant>& plane_fwd_registry() {
     // occupancy was not the limit: ncu shows the LSU data pipe 81 % busy in the two-buffer kernel, 85 % here (r2_plane.md)
     v.push_back(c2c64_ip_variant<256>());
     v.push_back(c2c64_ip_variant<512>());
+    v.push_back(c2c128_ip_variant<512>());
+    v.push_back(c2c128_ip_variant<1024>());
     v.push_back(r2c64_variant<256>());  // 6400 x 64 x 64 R2C: t256 0.0618, t128 0.0647, t64 0.0712 ms
     v.push_back(r2c64_variant<128>());
     v.push_back(r2c64_variant<64>());

@@ -22,6 +22,11 @@ CASES = [
     ((2, 3, 64, 64, 64), "c2c", False, False),
     ((2, 10, 64, 64), "half", False, False),
     ((3, 100, 64, 64), "c2c", True, False),          # outer axis on a run-time specialised strided kernel
+    # 128 x 128 planes: ONE shared buffer (139 KB, one CTA per SM), stages exchanged in place through registers
+    ((3, 128, 128, 128), "c2c", False, False),
+    ((2, 128, 128, 128), "c2c", True, False),
+    ((2, 128, 128, 128), "real", False, False),
+    ((5, 128, 128), "c2c", False, False),
 ]
 
 
@@ -37,7 +42,8 @@ def test_plane_plans(shape, mode, inverse, force, monkeypatch):
     rm = b200fft.REAL_HALF if mode == "half" else b200fft.REAL_FULL
     plan = b200fft.plan_fft("float32", "float32", x.shape, oshape, inverse=inverse, real_mode=rm)
     desc = plan.describe()
-    assert ("r2cplane64x64" if mode == "half" else "plane64x64") in desc.split("\n")[0] and not desc.startswith("fused"), desc
+    tag = "plane%dx%d" % (shape[-2], shape[-1])
+    assert (("r2c" + tag) if mode == "half" else tag) in desc.split("\n")[0] and not desc.startswith("fused"), desc
     assert plan.launches == len(shape) - 2
     xt = torch.from_numpy(x).cuda()
     keep = xt.clone()
@@ -53,7 +59,7 @@ def test_plane_plans(shape, mode, inverse, force, monkeypatch):
     want = np.fft.rfftn(xd[..., 0], axes=axes) if mode == "half" else (np.fft.ifftn(xc, axes=axes) if inverse else np.fft.fftn(xc, axes=axes))
     assert np.linalg.norm(got - want) <= 2e-6 * np.sqrt(len(axes)) * np.linalg.norm(want), desc
     plain = b200fft.plan_fft("float32", "float32", x.shape, oshape, inverse=inverse, real_mode=rm, flags=b200fft.FLAG_NO_FUSED)
-    assert "plane64x64" not in plain.describe()
+    assert tag not in plain.describe()
     out2 = torch.empty_like(out)
     b200fft.fft(out2, xt, plan=plain)
     torch.cuda.synchronize()
