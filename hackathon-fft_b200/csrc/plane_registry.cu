@@ -188,6 +188,27 @@ PlaneFwdVariant r2c64_variant() {
 }
 
 // order = preference; B200FFT_PLANE_PREFER=<substr> moves matching names to the front (tuning aid)
+template <int NY, int H, class RLY, class RLX, int NT>
+struct R2CPlaneIpV {
+  static void launch(bool, bool, const PlaneFwdArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    r2c_plane_ip_kernel<NY, H, RLY, RLX, NT><<<grid, NT, smem, st>>>(a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    return cudaFuncSetAttribute(r2c_plane_ip_kernel<NY, H, RLY, RLX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+};
+template <int NT, class RY>
+PlaneFwdVariant r2c128_ip_variant(const char* tag) {
+  using RX = Radices<8, 8>;
+  PlaneFwdVariant c;
+  c.r2c = true; c.ny = 128; c.nx = 64; c.ry = radix_vec<RY>(); c.rx = radix_vec<RX>(); c.threads = NT;
+  c.smem = r2c_plane_ip_smem_bytes<128, 64, RX>();
+  c.launch = &R2CPlaneIpV<128, 64, RY, RX, NT>::launch;
+  c.prepare = &R2CPlaneIpV<128, 64, RY, RX, NT>::prepare;
+  c.name = "r2cplane128x128(" + radix_name(c.ry) + ";2;8x8)_inplace_t" + std::to_string(NT) + tag;
+  return c;
+}
+
 const std::vector<PlaneFwdVariant>& plane_fwd_registry() {
   static const std::vector<PlaneFwdVariant> r = [] {
     std::vector<PlaneFwdVariant> v;
@@ -200,6 +221,9 @@ const std::vector<PlaneFwdVariant>& plane_fwd_registry() {
     v.push_back(c2c64_ip_variant<512>());
     v.push_back(c2c128_ip_variant<512>());
     v.push_back(c2c128_ip_variant<1024>());
+    v.push_back(r2c128_ip_variant<512, Radices<8, 16>>(""));
+    v.push_back(r2c128_ip_variant<512, Radices<16, 8>>("_y16x8"));
+    v.push_back(r2c128_ip_variant<256, Radices<8, 16>>(""));
     v.push_back(r2c64_variant<256>());  // 6400 x 64 x 64 R2C: t256 0.0618, t128 0.0647, t64 0.0712 ms
     v.push_back(r2c64_variant<128>());
     v.push_back(r2c64_variant<64>());

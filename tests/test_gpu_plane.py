@@ -27,6 +27,8 @@ CASES = [
     ((2, 128, 128, 128), "c2c", True, False),
     ((2, 128, 128, 128), "real", False, False),
     ((5, 128, 128), "c2c", False, False),
+    ((3, 128, 128, 128), "half", False, False),      # in-place R2C plane: the 65 bins of a row fit the 72-element pitch
+    ((6, 128, 128), "half", False, False),
 ]
 
 
