@@ -315,4 +315,55 @@ __global__ void __launch_bounds__(NT) r2c_plane_ip_kernel(const __grid_constant_
   run_stage<RLY::r[1], RLY::r[0], NY, 1, HB, NT, false>(SmemSrc<PitchColsDense<PX>>{B}, dst, a.twy + RLY::tw_offset(1), 1.f, false);
 }
 
+// In-place half-spectrum INVERSE plane (mirror of r2c_plane_ip_kernel): ONE buffer of NY rows with pitch PX = H + H / r0.
+// The block's NY x (H + 1) bins are loaded into it, both y stages run in place over the H + 1 columns, x stage 0 forms
+// Z[k] from the row's bins (Hermitian pack) and writes the H-point exchange layout in place, x stage 1 stores the real rows.
+template <int H, int PX>
+struct HermPitchSrc {
+  const float2* xb;  // rows of pitch PX holding H + 1 bins
+  const float2* __restrict__ tw2;
+  __device__ __forceinline__ float2 load(int o, int i, int) const {
+    const float2 xk = xb[o * PX + i];
+    float2 xm = xb[o * PX + H - i];
+    xm.y = -xm.y;
+    const float2 s = make_float2(xk.x + xm.x, xk.y + xm.y), d = make_float2(xk.x - xm.x, xk.y - xm.y);
+    const float2 t = cmulf(d, __ldg(&tw2[i]));
+    return make_float2(s.x - t.y, s.y + t.x);
+  }
+};
+
+template <int NY, int H, class RLY, class RLX, int NT>
+__global__ void __launch_bounds__(NT) c2r_plane_ip_kernel(const __grid_constant__ PlaneArgs a) {
+  static_assert(RLY::count == 2 && RLX::count == 2, "plane tiles: two super-stages per axis");
+  static_assert(RLY::product() == NY && RLX::product() == H, "radices must multiply to the axis lengths");
+  constexpr int HB = H + 1;
+  constexpr int PX = H + H / RLX::r[0];
+  static_assert(PX >= HB, "the H + 1 bins of a row must fit its pitch");
+  extern __shared__ __align__(16) float2 smem_f2[];
+  float2* B = smem_f2;
+  const long long p = blockIdx.x;
+  const float2* __restrict__ in = a.in + p * (long long)(NY * HB);
+  constexpr int TOTAL = NY * HB;
+  constexpr int ROUNDS = (TOTAL + NT - 1) / NT;
+#pragma unroll 8
+  for (int it = 0; it < ROUNDS; ++it) {
+    const int idx = (int)threadIdx.x + it * NT;
+    if (idx < TOTAL) {
+      const int y = idx / HB, c = idx - y * HB;
+      B[y * PX + c] = __ldg(&in[idx]);
+    }
+  }
+  __syncthreads();
+  using LC = PitchColsDense<PX>;
+  run_stage_inplace<RLY::r[0], 1, NY, 1, HB, NT, true>(SmemSrc<LC>{B}, SmemDst<LC>{B}, a.twy);
+  __syncthreads();
+  run_stage_inplace<RLY::r[1], RLY::r[0], NY, 1, HB, NT, true>(SmemSrc<LC>{B}, SmemDst<LC>{B}, a.twy + RLY::tw_offset(1));
+  __syncthreads();
+  using LR = PitchLayout<H, RLX::r[0]>;
+  run_stage_inplace<RLX::r[0], 1, H, NY, 1, NT, true>(HermPitchSrc<H, PX>{B, a.tw2}, SmemDst<LR>{B}, a.twx);
+  __syncthreads();
+  GlobalDst dst{a.out + p * (long long)(NY * H), H, 1, NY, 1};
+  run_stage<RLX::r[1], RLX::r[0], H, NY, 1, NT, true>(SmemSrc<LR>{B}, dst, a.twx + RLX::tw_offset(1), a.scale, true);
+}
+
 }  // namespace b200fft

@@ -48,9 +48,33 @@ PlaneVariant make_variant() {
   return v;
 }
 
+template <int NY, int H, class RLY, class RLX, int NT>
+void launch_plane_ip(const PlaneArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+  c2r_plane_ip_kernel<NY, H, RLY, RLX, NT><<<grid, NT, smem, st>>>(a);
+}
+template <int NY, int H, class RLY, class RLX, int NT>
+PlaneVariant make_ip_variant() {
+  PlaneVariant v;
+  v.ny = NY;
+  v.h = H;
+  v.ry = radix_vec<RLY>();
+  v.rx = radix_vec<RLX>();
+  v.threads = NT;
+  v.smem = r2c_plane_ip_smem_bytes<NY, H, RLX>();
+  v.launch = &launch_plane_ip<NY, H, RLY, RLX, NT>;
+  v.func = (const void*)c2r_plane_ip_kernel<NY, H, RLY, RLX, NT>;
+  v.name = "c2rplane" + std::to_string(NY) + "x" + std::to_string(2 * H) + "(" + radix_name(v.ry) + ";" + radix_name(v.rx) + ";2)_inplace_t" +
+           std::to_string(NT);
+  return v;
+}
+
 const std::vector<PlaneVariant>& plane_registry() {
   static const std::vector<PlaneVariant> r = [] {
     std::vector<PlaneVariant> v;
+    // 128 x 128 in ONE 74 KB buffer (three stages exchanged in place): 10 x 128^3 C2R 0.1155 ms vs 0.0951 ms per axis — opt-in
+    // like the two-buffer 133 KB variant below (B200FFT_PLANE_C2R=1), unlike its forward twin, which wins (r2_plane.md)
+    v.push_back(make_ip_variant<128, 64, Radices<8, 16>, Radices<8, 8>, 512>());
+    v.back().by_default = false;
     v.push_back(make_variant<64, 32, Radices<8, 8>, Radices<8, 4>, 128>());
     // 128 x 128: 133 KB of shared memory = one CTA per SM: 10 x 128^3 C2R 0.132 ms vs 0.096 ms per axis (profiles/r2_c2r.md)
     v.push_back(make_variant<128, 64, Radices<16, 8>, Radices<8, 8>, 256>());
