@@ -313,6 +313,16 @@ constexpr int max_exchange_elems() {
   }
 }
 
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// A pass that FOLLOWS another pass of a plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (fast_registry.hpp: launch_dependent): the driver may set its grid up while the previous pass is still running, and its
+// CTAs block in pdl_wait until that grid has completed and its writes are visible. For a kernel launched the ordinary way
+// pdl_wait is a no-op, so every tile kernel calls it first thing. The previous pass does NOT signal early
+// (griddepcontrol.launch_dependents at CTA start was measured: the same gain on most shapes, but the waiting CTAs it lets
+// in cost the real-input 2-D shape 3 % and, with plane kernels signalling too, 100 x 64^3 9 %; profiles/r2_pdl.md): what is
+// hidden is the launch latency of pass k+1, 2-5 us per boundary.   B200FFT_PDL=0: ordinary launches everywhere.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- kernels ------------------------------------------------------------------------------------
 struct RowsArgs {
   const void* in;
@@ -332,6 +342,7 @@ __global__ void __launch_bounds__(NT) rows_kernel(const __grid_constant__ RowsAr
   constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + BUF;
+  pdl_wait();
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
   const void* in = REAL ? (const void*)(reinterpret_cast<const in_scalar*>(a.in) + row0 * N)
@@ -477,6 +488,7 @@ __device__ __forceinline__ void r2c_tile(const in_vec2* in, float2* __restrict__
 template <int H, class RL, int C, int NT>
 __global__ void __launch_bounds__(NT) rows_r2c_kernel(const __grid_constant__ HalfArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
   r2c_tile<H, RL, C, NT>(reinterpret_cast<const in_vec2*>(a.in) + row0 * H,
@@ -537,6 +549,7 @@ template <int H, class RL, int C, int NT>
 __global__ void __launch_bounds__(NT) rows_r2c_reg_kernel(const __grid_constant__ HalfArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
   constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
+  pdl_wait();
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
   GlobalSrc<false> src{reinterpret_cast<const in_vec2*>(a.in) + row0 * H, H, 1, valid, 1};
@@ -559,6 +572,7 @@ template <int N, class RL, int C, int NT>
 __global__ void __launch_bounds__(NT) rows_r2c_odd_kernel(const __grid_constant__ HalfArgs a) {
   static_assert(N % 2 == 1, "odd lengths only (even lengths run as an n/2-point complex transform)");
   extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
   constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
@@ -591,6 +605,7 @@ struct HermGlobalSrc {
 template <int H, class RL, int C, int NT>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 3 : 1) rows_c2r_kernel(const __grid_constant__ HalfArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
   constexpr int EX = max_exchange_elems<RL, C, RowLayoutN<H>::template type>();
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + EX;
@@ -626,6 +641,7 @@ template <int N, class RL, int C, int NT>
 __global__ void __launch_bounds__(NT) rows_c2r_odd_kernel(const __grid_constant__ HalfArgs a) {
   static_assert(N % 2 == 1, "odd lengths only");
   extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
   constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
   const long long row0 = (long long)blockIdx.x * C;
   const int valid = (int)min((long long)C, a.nrows - row0);
@@ -664,6 +680,7 @@ __global__ void __launch_bounds__(NT) cols_kernel(const __grid_constant__ ColsAr
   constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + BUF;
+  pdl_wait();
   const unsigned bid = a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const long long o = bid / a.tiles_per_outer;
   const long long c0 = (long long)(bid - o * a.tiles_per_outer) * CW;
@@ -704,6 +721,7 @@ template <int N, class RL, int CW, int NT, bool INV>
 __global__ void __launch_bounds__(NT) cols_scatter_kernel(const __grid_constant__ ColsArgs a,
                                                           const __grid_constant__ ScatterArgs sa) {
   extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
   constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
   float2* buf0 = smem_f2;
   float2* buf1 = smem_f2 + BUF;
@@ -761,6 +779,7 @@ struct SplitTwDst {
 template <int N, class RL, int CW, int NT, bool INV>
 __global__ void __launch_bounds__(NT) cols_split_a_kernel(const __grid_constant__ SplitArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
   constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
   const long long vinner = (long long)a.n2 * a.inner;
   const long long o = blockIdx.x / a.tiles_per_outer;
@@ -776,6 +795,7 @@ __global__ void __launch_bounds__(NT) cols_split_a_kernel(const __grid_constant_
 template <int N, class RL, int CW, int NT, bool INV>
 __global__ void __launch_bounds__(NT) cols_split_b_kernel(const __grid_constant__ SplitArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
   constexpr int BUF = max_exchange_elems<RL, 1, DenseLayoutN<N, CW>::template type>();
   const long long ov = blockIdx.x / a.tiles_per_outer;  // o * n1 + k1
   const long long c0 = (long long)(blockIdx.x - ov * a.tiles_per_outer) * CW;
@@ -791,6 +811,7 @@ __global__ void __launch_bounds__(NT) cols_split_b_kernel(const __grid_constant_
 template <int N, class RL, int C, int NT, bool INV>
 __global__ void __launch_bounds__(NT) rows_split_b_kernel(const __grid_constant__ SplitArgs a) {
   extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
   constexpr int BUF = max_exchange_elems<RL, C, RowLayoutN<N>::template type>();
   const long long row0 = (long long)blockIdx.x * C;  // rows never straddle transforms: C divides n1
   const int valid = (int)min((long long)C, a.nrows - row0);

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "fast.cuh"
@@ -56,6 +58,28 @@ bool encode_axis_map(CUtensorMap* map, const void* base, long long inner, long l
 bool tensor_maps_available();
 
 
+// Launch a pass whose grid may be set up while the previous pass of the same stream is still running (fast.cuh: pdl_wait).
+// Used for the passes that FOLLOW another pass of a plan (strided passes, the C2R row pass). Measured (profiles/r2_pdl.md):
+// 256^3 0.126 -> 0.122 ms, its R2C 0.071 -> 0.066, 2-D 640 x 480 0.161 -> 0.158, 100 x 64^3 0.149 -> 0.146.
+inline bool pdl_enabled() {
+  const char* e = getenv("B200FFT_PDL");  // read per launch (~50 ns): lets one process A/B the two launch modes
+  return !(e && atoi(e) == 0);
+}
+template <class... KArgs, class... Args>
+void launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // FULL variants instantiate forward/inverse x complex/real-input; tuning candidates only
 // forward complex (they are skipped for other requests).
 // VEC: complex-input instantiations use 128-bit global accesses + shuffle exchange (real input keeps 32-bit loads)
@@ -85,7 +109,7 @@ struct RowsV {
 template <int H, class RL, int C, int NT>
 struct HalfV {
   static void launch(bool c2r, const HalfArgs& a, unsigned grid, cudaStream_t st) {
-    if (c2r) rows_c2r_kernel<H, RL, C, NT><<<grid, NT, rows_c2r_smem_bytes<H, RL, C>(), st>>>(a);
+    if (c2r) launch_dependent(rows_c2r_kernel<H, RL, C, NT>, grid, NT, rows_c2r_smem_bytes<H, RL, C>(), st, a);  // last pass of a C2R plan
     else rows_r2c_kernel<H, RL, C, NT><<<grid, NT, rows_r2c_smem_bytes<H, RL, C>(), st>>>(a);
   }
   static cudaError_t prepare() {
@@ -113,7 +137,7 @@ struct HalfOddV {
     rows_r2c_odd_kernel<N, RL, C, NT><<<grid, NT, smem, st>>>(a);
   }
   static void launch_c2r(const HalfArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
-    rows_c2r_odd_kernel<N, RL, C, NT><<<grid, NT, smem, st>>>(a);
+    launch_dependent(rows_c2r_odd_kernel<N, RL, C, NT>, grid, NT, smem, st, a);  // last pass of a C2R plan
   }
   static cudaError_t prepare(size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
@@ -127,11 +151,11 @@ template <int N, class RL, int CW, int NT, bool FULL>
 struct ColsV {
   static void launch(bool inv, bool real, const ColsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
     if constexpr (FULL) {
-      if (!inv && real) return (void)cols_kernel<N, RL, CW, NT, false, true><<<grid, NT, smem, st>>>(a);
-      if (inv && !real) return (void)cols_kernel<N, RL, CW, NT, true, false><<<grid, NT, smem, st>>>(a);
-      if (inv && real) return (void)cols_kernel<N, RL, CW, NT, true, true><<<grid, NT, smem, st>>>(a);
+      if (!inv && real) return launch_dependent(cols_kernel<N, RL, CW, NT, false, true>, grid, NT, smem, st, a);
+      if (inv && !real) return launch_dependent(cols_kernel<N, RL, CW, NT, true, false>, grid, NT, smem, st, a);
+      if (inv && real) return launch_dependent(cols_kernel<N, RL, CW, NT, true, true>, grid, NT, smem, st, a);
     }
-    cols_kernel<N, RL, CW, NT, false, false><<<grid, NT, smem, st>>>(a);
+    launch_dependent(cols_kernel<N, RL, CW, NT, false, false>, grid, NT, smem, st, a);
   }
   static cudaError_t prepare(size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
