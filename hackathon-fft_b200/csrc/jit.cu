@@ -100,6 +100,7 @@ struct Driver {
   CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**,
                            void**) = nullptr;
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;  // optional (dependent launches)
   bool ok = false;
 };
 
@@ -122,6 +123,7 @@ const Driver& driver() {
     d.FuncSetAttribute = reinterpret_cast<decltype(d.FuncSetAttribute)>(get("cuFuncSetAttribute"));
     d.FuncGetAttribute = reinterpret_cast<decltype(d.FuncGetAttribute)>(get("cuFuncGetAttribute"));
     d.LaunchKernel = reinterpret_cast<decltype(d.LaunchKernel)>(get("cuLaunchKernel"));
+    d.LaunchKernelEx = reinterpret_cast<decltype(d.LaunchKernelEx)>(get("cuLaunchKernelEx"));
     d.ok = d.ModuleLoadData && d.ModuleUnload && d.ModuleGetFunction && d.ModuleGetGlobal && d.FuncSetAttribute && d.FuncGetAttribute && d.LaunchKernel;
     return d;
   }();
@@ -577,8 +579,29 @@ struct JitPass : Pass {
   int run(const JitKernel& kern, const JitSpec& sp, long long grid, void** params, cudaStream_t stream) {
     if (grid <= 0) return B200FFT_OK;
     if (grid > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many tiles");
-    const CUresult r = driver().LaunchKernel(kern.fn, (unsigned)grid, 1, 1, (unsigned)sp.threads, 1, 1, (unsigned)sp.smem(),
-                                             (CUstream)stream, params, nullptr);
+    // a pass that follows another pass of the plan: programmatic dependent launch (fast.cuh: pdl_wait; profiles/r2_pdl.md)
+    const bool dependent = (sp.kind == JIT_COLS || sp.kind == JIT_C2R || sp.kind == JIT_C2R_ODD) && driver().LaunchKernelEx && pdl_enabled();
+    CUresult r;
+    if (dependent) {
+      CUlaunchConfig cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDimX = (unsigned)grid;
+      cfg.gridDimY = cfg.gridDimZ = 1;
+      cfg.blockDimX = (unsigned)sp.threads;
+      cfg.blockDimY = cfg.blockDimZ = 1;
+      cfg.sharedMemBytes = (unsigned)sp.smem();
+      cfg.hStream = (CUstream)stream;
+      CUlaunchAttribute attr;
+      memset(&attr, 0, sizeof attr);
+      attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+      attr.value.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      r = driver().LaunchKernelEx(&cfg, kern.fn, params, nullptr);
+    } else {
+      r = driver().LaunchKernel(kern.fn, (unsigned)grid, 1, 1, (unsigned)sp.threads, 1, 1, (unsigned)sp.smem(), (CUstream)stream, params,
+                                nullptr);
+    }
     if (r != CUDA_SUCCESS) return fail(B200FFT_ERR_CUDA, "launch of %s failed (CUresult %d)", sp.name().c_str(), (int)r);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return B200FFT_OK;
