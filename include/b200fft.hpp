@@ -198,6 +198,63 @@ inline Plan plan_fft(DType in_dtype, DType out_dtype, const Layout& in_layout, c
 // asynchronous on `stream`, device pointers with the plan's layouts, caller synchronises (fft/bench.mojo:51-52).
 inline void fft(void* output, const void* x, void* stream, const Plan& plan) { plan.exec(output, x, stream); }
 
+// One host process, several GPUs (b200fft_mgpu_*): batch sharding without communication, or the slab decomposition of ONE
+// 3-D complex fp32 transform (dims (Z, Y, X); slot g holds z planes [g Z/G, (g+1) Z/G), the result is Y-slab distributed).
+enum class MultiGpuMode { batch_shard = B200FFT_MGPU_BATCH_SHARD, slab = B200FFT_MGPU_SLAB };
+
+class MultiGpuPlan {
+ public:
+  MultiGpuPlan() = default;
+  MultiGpuPlan(DType in_dtype, DType out_dtype, const Layout& in_layout, const Layout& out_layout, const std::vector<int>& devices,
+               MultiGpuMode mode = MultiGpuMode::batch_shard, const PlanOptions& options = PlanOptions()) {
+    detail::Marshalled m;
+    detail::marshal(in_dtype, out_dtype, in_layout, out_layout, options, &m);
+    check(b200fft_mgpu_plan_create(&h_, &m.desc, (int)devices.size(), devices.data(), (int)mode));
+  }
+  MultiGpuPlan(MultiGpuPlan&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  MultiGpuPlan& operator=(MultiGpuPlan&& o) noexcept {
+    if (this != &o) {
+      reset();
+      h_ = o.h_;
+      o.h_ = nullptr;
+    }
+    return *this;
+  }
+  MultiGpuPlan(const MultiGpuPlan&) = delete;
+  MultiGpuPlan& operator=(const MultiGpuPlan&) = delete;
+  ~MultiGpuPlan() { reset(); }
+
+  int ngpu() const { return b200fft_mgpu_ngpu(h_); }
+  // (first, count) of the batch items (batch shard) / z planes (slab) device slot g holds
+  std::pair<int64_t, int64_t> shard(int g) const {
+    int64_t first = 0, count = 0;
+    check(b200fft_mgpu_shard(h_, g, &first, &count));
+    return {first, count};
+  }
+  size_t in_bytes(int g) const { return b200fft_mgpu_in_bytes(h_, g); }
+  size_t out_bytes(int g) const { return b200fft_mgpu_out_bytes(h_, g); }
+  // enqueue on every slot's plan-owned stream (d_out[g] / d_in[g] live on slot g's device); synchronize() before reading
+  void exec(void* const* d_out, const void* const* d_in) const { check(b200fft_mgpu_exec(h_, d_out, d_in)); }
+  void synchronize() const { check(b200fft_mgpu_synchronize(h_)); }
+  void* stream(int g) const { return b200fft_mgpu_stream(h_, g); }
+  // the whole job from / to host memory in natural order; returns when h_out is complete
+  void exec_host(void* h_out, const void* h_in) const { check(b200fft_mgpu_exec_host(h_, h_out, h_in)); }
+  std::string describe() const {
+    std::string s(b200fft_mgpu_describe(h_, nullptr, 0), '\0');
+    if (!s.empty()) b200fft_mgpu_describe(h_, &s[0], s.size());
+    while (!s.empty() && s.back() == '\0') s.pop_back();
+    return s;
+  }
+  explicit operator bool() const { return h_ != nullptr; }
+
+ private:
+  void reset() {
+    if (h_) b200fft_mgpu_plan_destroy(h_);
+    h_ = nullptr;
+  }
+  b200fft_mgpu_plan* h_ = nullptr;
+};
+
 // Validate a request and return the pass list it would produce, without touching CUDA.
 inline std::string dry_run(DType in_dtype, DType out_dtype, const Layout& in_layout, const Layout& out_layout,
                            const PlanOptions& options = PlanOptions()) {

@@ -199,6 +199,13 @@ int main() {
     if (e.status() != B200FFT_ERR_CUDA) return 15;   // no sm_100 device: loud failure, never a CPU path
     std::printf("no-gpu: %s\n", e.what());
   }
+  try {   // the multi-device layer: same loud failure without GPUs, a working plan with them
+    MultiGpuPlan mp(f32, f32, Layout{{8, 128, 2}}, Layout{{8, 128, 2}}, {0}, MultiGpuMode::batch_shard);
+    MultiGpuPlan mq = std::move(mp);
+    if (mp || !mq || mq.ngpu() != 1 || mq.shard(0) != std::pair<int64_t, int64_t>(0, 8) || mq.in_bytes(0) != 8 * 128 * 8) return 16;
+  } catch (const Error& e) {
+    if (e.status() != B200FFT_ERR_CUDA) return 17;
+  }
   return 0;
 }
 ''')
