@@ -42,7 +42,14 @@ KERNELS = [
     ("rt_axis_fwd_r16", r"rt_axis_kernel<false, 16>"),
     ("c2r512_32x16", r"rows_c2r_kernel<512, b200fft::Radices<32, 16>, 8, 256>"),
     ("gen_fft_f32", r"gen_fft_kernel<float>"),
+    # plane kernels (csrc/plane.cuh)
+    ("c2c_plane64x64_fwd", r"c2c_plane_kernel<64, 64, b200fft::Radices<8, 8>, b200fft::Radices<8, 8>, 256, false, false>"),
+    ("r2c_plane64x64", r"r2c_plane_kernel<64, 32, b200fft::Radices<8, 8>, b200fft::Radices<8, 4>, 256>"),
+    ("c2r_plane64x64", r"c2r_plane_kernel<64, 32, b200fft::Radices<8, 8>, b200fft::Radices<8, 4>, 128>"),
+    ("c2c_plane128x128_inplace_fwd", r"c2c_plane_ip_kernel<128, 128, b200fft::Radices<16, 8>, b200fft::Radices<16, 8>, 512, false, false>"),
+    ("r2c_plane128x128_inplace", r"r2c_plane_ip_kernel<128, 64, b200fft::Radices<8, 16>, b200fft::Radices<8, 8>, 512>"),
 ]
+MAX_LINES = 6000  # longer listings (the runtime-length kernel unrolls 31 codelets: 25 MB) are cut here; the histogram counts all of it
 
 # plan-time specialised kernels (csrc/jit.cu): compiled here with NVRTC through b200fft_jit_probe (no GPU needed), the
 # cubins kept by B200FFT_JIT_DUMP_DIR. (file name, probe arguments)
@@ -112,7 +119,9 @@ def main():
         body = funcs[hit[0]]
         with open(os.path.join(OUT, fname + ".sass"), "w") as f:
             f.write("// %s\n" % dem[names.index(hit[0])])
-            f.write("\n".join(body) + "\n")
+            f.write("\n".join(body[:MAX_LINES]) + "\n")
+            if len(body) > MAX_LINES:
+                f.write("// ... %d more lines not kept (tools/dump_sass.py regenerates the full listing)\n" % (len(body) - MAX_LINES))
         ops = collections.Counter()
         for line in body:
             m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
