@@ -456,8 +456,16 @@ constexpr int JIT_MAX_STAGES = 5;
 bool jit_group_cap(const std::vector<uint32_t>& ordered, int cap, std::vector<int>* out, int max_stages = JIT_MAX_STAGES) {
   std::vector<uint32_t> small;
   std::vector<int> big;
+  auto is_prime = [](uint32_t r) {
+    for (uint32_t f = 2; f * f <= r; ++f)
+      if (r % f == 0) return false;
+    return r > 1;
+  };
   for (uint32_t r : ordered) {
     if (r > (uint32_t)JIT_MAX_PRIME) return false;
+    // a user base above the cap is a stage of its own: primes up to JIT_MAX_PRIME (looped above 64), composites up to 64 (a
+    // fully unrolled Cooley-Tukey codelet; larger ones would take NVRTC tens of seconds and 200+ registers)
+    if (r > (uint32_t)cap && !is_prime(r) && r > 64) return false;
     if (r > (uint32_t)cap) big.push_back((int)r);
     else small.push_back(r);
   }
