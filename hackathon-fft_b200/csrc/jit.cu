@@ -33,6 +33,7 @@
 
 #include "fast_registry.hpp"
 #include "plan.hpp"
+#include "plane.cuh"
 
 namespace b200fft {
 
@@ -143,13 +144,18 @@ enum JitKind {
   // long axes as two passes, N = N1 * N2 (fast.cuh, "four-step"):
   JIT_SPLIT_A,      // cols_split_a_kernel<N1, RL, CW, NT, INV>: N1-point strided transforms, W_N^{k1 n2} fused into the store
   JIT_SPLIT_B_COLS, // cols_split_b_kernel<N2, RL, CW, NT, INV>: N2-point strided transforms, natural-order store
-  JIT_SPLIT_B_ROWS  // rows_split_b_kernel<N2, RL, C, NT, INV>: the same for a contiguous axis
+  JIT_SPLIT_B_ROWS, // rows_split_b_kernel<N2, RL, C, NT, INV>: the same for a contiguous axis
+  // the two innermost axes in one in-place tile per (y, x) plane (plane.cuh); n = NY, n2 = NX (R2C: H), radices = y, radices2 = x
+  JIT_PLANE_C2C,    // c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, INV, REAL>
+  JIT_PLANE_R2C     // r2c_plane_ip_kernel<NY, H, RLY, RLX, NT>
 };
 
 struct JitSpec {
   JitKind kind = JIT_ROWS;
   int n = 0;  // length of the complex transform the kernel runs (H = n_real / 2 for R2C / R2C_REG / C2R)
   std::vector<int> radices;
+  int n2 = 0;                  // plane kinds: the x extent (R2C: H)
+  std::vector<int> radices2;   // plane kinds: the x stages
   int tile = 0, threads = 0;
   bool inverse = false, real_in = false, packed = false;
   bool f64 = false;            // working precision (the plan's out_dtype): fp64 = the same kernels with the scalar type swapped
@@ -157,6 +163,13 @@ struct JitSpec {
 
   size_t esz() const { return f64 ? sizeof(double2) : sizeof(float2); }
   int tile_divides = 0;        // geometry only: the tile must divide this (split pass B rows never straddle transforms)
+  bool plane() const { return kind == JIT_PLANE_C2C || kind == JIT_PLANE_R2C; }
+  std::string plane_args() const {  // "<NY, NX, Radices<y...>, Radices<x...>"
+    std::string ry, rx;
+    for (int r : radices) ry += (ry.empty() ? "" : ", ") + std::to_string(r);
+    for (int r : radices2) rx += (rx.empty() ? "" : ", ") + std::to_string(r);
+    return std::to_string(n) + ", " + std::to_string(n2) + ", b200fft::Radices<" + ry + ">, b200fft::Radices<" + rx + ">";
+  }
   bool strided() const { return kind == JIT_COLS || kind == JIT_SCATTER || kind == JIT_SPLIT_A || kind == JIT_SPLIT_B_COLS; }
   std::string radix_list() const {
     std::string s;
@@ -171,6 +184,8 @@ struct JitSpec {
     const char* inv = inverse ? "true" : "false";
     const char* real = real_in ? "true" : "false";
     switch (kind) {
+      case JIT_PLANE_C2C: return "b200fft::c2c_plane_ip_kernel<" + plane_args() + ", " + std::to_string(threads) + ", " + inv + ", " + real + ">";
+      case JIT_PLANE_R2C: return "b200fft::r2c_plane_ip_kernel<" + plane_args() + ", " + std::to_string(threads) + ">";
       case JIT_ROWS: return "b200fft::rows_kernel<" + head + ", " + inv + ", " + real + ">";
       case JIT_COLS: return "b200fft::cols_kernel<" + head + ", " + inv + ", " + real + ">";
       case JIT_SCATTER: return "b200fft::cols_scatter_kernel<" + head + ", " + inv + ">";
@@ -186,6 +201,12 @@ struct JitSpec {
   }
   std::string smem_expression() const {  // fast.cuh's own constexpr for the instantiation's dynamic shared memory
     switch (kind) {
+      case JIT_PLANE_C2C:
+        return "b200fft::c2c_plane_ip_smem_bytes<" + std::to_string(n) + ", " + std::to_string(n2) + ", b200fft::Radices<" +
+               std::to_string(radices2[0]) + ", " + std::to_string(radices2[1]) + ">>()";
+      case JIT_PLANE_R2C:
+        return "b200fft::r2c_plane_ip_smem_bytes<" + std::to_string(n) + ", " + std::to_string(n2) + ", b200fft::Radices<" +
+               std::to_string(radices2[0]) + ", " + std::to_string(radices2[1]) + ">>()";
       case JIT_ROWS:
       case JIT_SPLIT_B_ROWS:
       case JIT_C2R_ODD:
@@ -201,7 +222,10 @@ struct JitSpec {
   }
   std::string name() const {
     static const char* const tag[] = {"jitrows", "jitcols", "jitscatter", "jitr2c", "jitr2creg", "jitr2codd", "jitc2r", "jitc2rodd",
-                                      "jitsplitA", "jitsplitBcols", "jitsplitBrows"};
+                                      "jitsplitA", "jitsplitBcols", "jitsplitBrows", "jitplane", "jitr2cplane"};
+    if (plane())
+      return std::string(tag[kind]) + std::to_string(n) + "x" + std::to_string(kind == JIT_PLANE_R2C ? 2 * n2 : n2) + "(" + radix_name(radices) +
+             ";" + radix_name(radices2) + ")_inplace_t" + std::to_string(threads) + (f64 ? "_f64" : "");
     return std::string(tag[kind]) + std::to_string(n) + "_" + radix_name(radices) + (strided() ? "_w" : "_c") + std::to_string(tile) +
            "_t" + std::to_string(threads) + (f64 ? "_f64" : "") + (in_dtype == B200FFT_U8 ? "_inu8" : in_dtype == (f64 ? B200FFT_F32 : B200FFT_F64) ? (f64 ? "_inf32" : "_inf64") : "");
   }
@@ -218,6 +242,7 @@ struct JitSpec {
   // checked against the value the compiled module reports (b200fft_jit_smem_bytes) when it is loaded.
   // RowLayout pads a Q-block by P elements when P < 16, Q even and Q < N; DenseLayout is N x CW.
   size_t smem() const {
+    if (plane()) return esz() * (size_t)n * (size_t)(n2 + n2 / radices2[0]);  // one buffer of NY rows, pitch NX + NX / r0
     long long P = 1, ex = 0;
     for (size_t s = 0; s + 1 < radices.size(); ++s) {
       const long long Q = P * radices[s];
@@ -253,12 +278,12 @@ int compile(const JitSpec& spec, std::vector<char>* cubin, std::string* lowered,
   if (!rtc.ok) return fail(B200FFT_ERR_UNSUPPORTED, "run-time compilation unavailable: %s", rtc.why.c_str());
   const auto t0 = std::chrono::steady_clock::now();
   std::string src = spec.defines();
-  src += "#include \"fast.cuh\"\n";
+  src += "#include \"fast.cuh\"\n#include \"plane.cuh\"\n";
   src += "extern \"C\" __device__ unsigned long long b200fft_jit_smem_bytes = (unsigned long long)" + spec.smem_expression() + ";\n";
-  const char* headers[] = {k_src_rtc_prelude, k_src_dft, k_src_tma, k_src_fast};
-  const char* names[] = {"rtc_prelude.cuh", "dft.cuh", "tma.cuh", "fast.cuh"};
+  const char* headers[] = {k_src_rtc_prelude, k_src_dft, k_src_tma, k_src_fast, k_src_plane};
+  const char* names[] = {"rtc_prelude.cuh", "dft.cuh", "tma.cuh", "fast.cuh", "plane.cuh"};
   Nvrtc::Program prog = nullptr;
-  int rc = rtc.CreateProgram(&prog, src.c_str(), "b200fft_jit.cu", 4, headers, names);
+  int rc = rtc.CreateProgram(&prog, src.c_str(), "b200fft_jit.cu", 5, headers, names);
   if (rc) return fail(B200FFT_ERR_CUDA, "nvrtcCreateProgram: %s", rtc.GetErrorString(rc));
   const std::string expr = spec.expression();
   rc = rtc.AddNameExpression(prog, expr.c_str());
@@ -326,7 +351,8 @@ std::string disk_cache_path(const JitSpec& spec) {
     uint64_t h = fnv1a(k_src_rtc_prelude, strlen(k_src_rtc_prelude));
     h = fnv1a(k_src_dft, strlen(k_src_dft), h);
     h = fnv1a(k_src_tma, strlen(k_src_tma), h);
-    return fnv1a(k_src_fast, strlen(k_src_fast), h);
+    h = fnv1a(k_src_fast, strlen(k_src_fast), h);
+    return fnv1a(k_src_plane, strlen(k_src_plane), h);
   }();
   static const std::string dir = disk_cache_dir();
   if (dir.empty()) return "";
@@ -991,6 +1017,122 @@ std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView
            half == HALF_R2C ? (spec.kind == JIT_R2C_ODD ? " r2c (real rows, bins 0..n/2 stored)" : " r2c")
            : half == HALF_C2R ? (spec.kind == JIT_C2R_ODD ? " c2r (Hermitian-extended load)" : " c2r") : spec.real_in ? " real-in" : "",
            k->compile_ms);
+  pass->text = buf;
+  return pass;
+}
+
+// ---- plane passes for plane sizes without a registered variant: the in-place plane kernels of plane.cuh specialised at
+// plan time (any NY x NX whose axes each split into two register stages and whose padded plane fits shared memory) ------
+namespace {
+
+struct JitPlanePass : Pass {
+  JitSpec spec;
+  std::shared_ptr<JitKernel> k;
+  long long planes_per_batch = 1;
+  float scale = 1.f;
+  void *twx = nullptr, *twy = nullptr, *tw2 = nullptr;
+  std::string text;
+  int launch(const void* src, void* dst, int64_t nbatch, cudaStream_t stream) override {
+    PlaneFwdArgs a;
+    a.in = src;
+    a.out = reinterpret_cast<float2*>(dst);
+    a.twx = reinterpret_cast<const float2*>(twx);
+    a.twy = reinterpret_cast<const float2*>(twy);
+    a.tw2 = reinterpret_cast<const float2*>(tw2);
+    a.planes = nbatch * planes_per_batch;
+    a.scale = scale;
+    a.do_scale = spec.inverse ? 1 : 0;
+    if (a.planes <= 0) return B200FFT_OK;
+    if (a.planes > 0x7fffffffLL) return fail(B200FFT_ERR_UNSUPPORTED, "too many planes");
+    void* params[1] = {&a};
+    const CUresult r = driver().LaunchKernel(k->fn, (unsigned)a.planes, 1, 1, (unsigned)spec.threads, 1, 1, (unsigned)spec.smem(),
+                                             (CUstream)stream, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(B200FFT_ERR_CUDA, "launch of %s failed (CUresult %d)", spec.name().c_str(), (int)r);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return B200FFT_OK;
+  }
+  std::string describe() const override { return text; }
+};
+
+// exactly two register stages of at most 32 for one axis, or false
+bool two_stages(const std::vector<uint32_t>& ordered, std::vector<int>* out) {
+  std::vector<uint32_t> bases(ordered);
+  std::sort(bases.begin(), bases.end(), [](uint32_t x, uint32_t y) { return x > y; });
+  long long g[2] = {1, 1};
+  for (uint32_t b : bases) {  // longest-processing-time rule into exactly two groups of product <= 32
+    const int i = g[0] <= g[1] ? 0 : 1;
+    if (g[i] * b <= JIT_MAX_RADIX) g[i] *= b;
+    else if (g[1 - i] * b <= JIT_MAX_RADIX) g[1 - i] *= b;
+    else return false;
+  }
+  if (g[0] < 2 || g[1] < 2) return false;
+  out->assign({(int)std::max(g[0], g[1]), (int)std::min(g[0], g[1])});
+  return true;
+}
+
+}  // namespace
+
+std::unique_ptr<Pass> make_jit_plane_pass(b200fft_plan& plan) {
+  const Problem& p = plan.prob;
+  if (!jit_enabled() || p.rank < 2 || (p.half && p.desc.inverse)) return nullptr;
+  if (const char* e = getenv("B200FFT_JIT_PLANE"))
+    if (atoi(e) == 0) return nullptr;
+  if (p.desc.out_dtype != B200FFT_F32 || p.desc.in_dtype != B200FFT_F32) return nullptr;
+  const int last = p.rank - 1;
+  if (!p.axes[last].transformed || !p.axes[last - 1].transformed) return nullptr;
+  const bool real_in = !p.half && p.desc.in_components == 1;
+  if (real_in && p.desc.inverse) return nullptr;
+  if (p.half && p.axes[last].n % 2) return nullptr;
+  JitSpec spec;
+  spec.kind = p.half ? JIT_PLANE_R2C : JIT_PLANE_C2C;
+  spec.n = (int)p.axes[last - 1].n;
+  spec.n2 = (int)(p.half ? p.axes[last].n / 2 : p.axes[last].n);
+  spec.inverse = p.desc.inverse != 0;
+  spec.real_in = real_in;
+  if ((long long)spec.n * spec.n2 < 256 || spec.n > 1024 || spec.n2 > 1024) return nullptr;
+  if (!two_stages(p.axes[last - 1].ordered, &spec.radices)) return nullptr;
+  if (p.half) {
+    bool ok = false;
+    for (const auto& o : drop_factor_two(p.axes[last].ordered))
+      if (two_stages(o, &spec.radices2)) { ok = true; break; }
+    if (!ok) return nullptr;
+  } else if (!two_stages(p.axes[last].ordered, &spec.radices2)) {
+    return nullptr;
+  }
+  spec.packed = true;
+  if (spec.smem() > 150 * 1024) return nullptr;
+  // threads: every in-place stage must hold its share of the tile in registers (run_stage_inplace: ROUNDS * R <= 40)
+  const long long cols = p.half ? spec.n2 + 1 : spec.n2;
+  const long long total_x1 = (long long)spec.n * (spec.n2 / spec.radices2[1]);
+  const long long total_y0 = (long long)(spec.n / spec.radices[0]) * cols;
+  spec.threads = 0;
+  for (int nt : {128, 256, 512, 1024}) {
+    const long long rx = (total_x1 + nt - 1) / nt * spec.radices2[1], ry = (total_y0 + nt - 1) / nt * spec.radices[0];
+    if (rx <= 40 && ry <= 40 && rx <= 32 + 8 && ry <= 32 + 8) {
+      spec.threads = nt;
+      if (nt >= 256 || (rx <= 16 && ry <= 16)) break;  // prefer >= 256 threads unless the tile is small
+    }
+  }
+  if (!spec.threads) return nullptr;
+  std::shared_ptr<JitKernel> k = get_kernel(spec, plan.device);
+  if (!k) return nullptr;
+  auto pass = std::make_unique<JitPlanePass>();
+  pass->spec = spec;
+  pass->k = k;
+  pass->planes_per_batch = 1;
+  for (int a = 0; a < last - 1; ++a) pass->planes_per_batch *= p.axes[a].n;
+  pass->scale = spec.inverse ? (float)(1.0 / ((double)spec.n * spec.n2)) : 1.f;
+  auto upload = [&](const std::vector<float2>& t, void** d) {
+    if (cudaMalloc(d, t.size() * sizeof(float2)) != cudaSuccess) { cudaGetLastError(); return false; }
+    plan.owned_device.push_back(*d);
+    return cudaMemcpy(*d, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  if (!upload(build_twiddles(spec.radices, spec.inverse), &pass->twy) || !upload(build_twiddles(spec.radices2, spec.inverse), &pass->twx))
+    return nullptr;
+  if (p.half && !upload(build_half_twiddles(p.axes[last].n, false), &pass->tw2)) return nullptr;
+  char buf[360];
+  snprintf(buf, sizeof buf, "axes %d,%d: %s: one in-place tile per (y, x) plane%s, smem=%zuB regs=%d [NVRTC, %.0f ms]", last - 1, last,
+           spec.name().c_str(), real_in ? " real-in" : "", spec.smem(), k->regs, k->compile_ms);
   pass->text = buf;
   return pass;
 }

@@ -126,6 +126,8 @@ std::unique_ptr<Pass> make_fused_pass(b200fft_plan& plan);
 std::unique_ptr<Pass> make_plane_c2r_pass(b200fft_plan& plan);
 // forward half spectrum / complex / real input: the two innermost axes in one tile per plane, or nullptr
 std::unique_ptr<Pass> make_plane_fwd_pass(b200fft_plan& plan);
+// ... the same for plane sizes without a registered variant, specialised at plan time (jit.cu)
+std::unique_ptr<Pass> make_jit_plane_pass(b200fft_plan& plan);
 // plan-time specialisation (jit.cu): the compile-time kernels instantiated through NVRTC for unregistered lengths
 std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView& view, const IoSpec& src, bool scale_inverse,
                                     HalfMode half);

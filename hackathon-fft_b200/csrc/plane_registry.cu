@@ -342,7 +342,7 @@ std::unique_ptr<Pass> make_plane_fwd_pass(b200fft_plan& plan) {
     pass->text = buf;
     return pass;
   }
-  return nullptr;
+  return make_jit_plane_pass(plan);  // no registered plane size: specialise one at plan time when the plane fits
 }
 
 // the two innermost axes of a half-spectrum inverse as one pass, or nullptr when no variant covers them

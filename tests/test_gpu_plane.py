@@ -71,10 +71,51 @@ def test_plane_plans(shape, mode, inverse, force, monkeypatch):
 
 
 def test_plane_respects_user_bases_and_knob(monkeypatch):
-    p = b200fft.plan_fft("float32", "float32", (4, 64, 64, 2), (4, 64, 64, 2), bases=[[4], [4]])   # [4,4,4] cannot form 8 x 8
-    assert "plane64x64" not in p.describe()
+    p = b200fft.plan_fft("float32", "float32", (4, 64, 64, 2), (4, 64, 64, 2), bases=[[4], [4]])   # [4,4,4] cannot form 8 x 8:
+    assert "plane64x64(8x8" not in p.describe() and "jitplane64x64(16x4;16x4)" in p.describe(), p.describe()   # specialised as 16 x 4
     p.destroy()
     monkeypatch.setenv("B200FFT_PLANE", "0")
     p = b200fft.plan_fft("float32", "float32", (4, 64, 64, 2), (4, 64, 64, 2))
     assert "plane64x64" not in p.describe()
     p.destroy()
+
+
+JIT_PLANES = [
+    # shape, mode, inverse: plane sizes without a registered variant -> in-place plane kernel specialised at plan time
+    ((6, 100, 100, 100), "c2c", False),
+    ((3, 100, 100, 100), "c2c", True),
+    ((5, 48, 48, 48), "c2c", False),
+    ((2, 96, 96, 96), "c2c", False),
+    ((7, 50, 60), "c2c", False),
+    ((4, 100, 100, 100), "half", False),
+    ((9, 48, 96), "half", False),
+    ((3, 32, 32, 32), "real", False),
+    ((2, 3, 60, 100), "c2c", False),
+]
+
+
+@pytest.mark.parametrize("shape,mode,inverse", JIT_PLANES)
+def test_plane_kernels_specialised_at_plan_time(shape, mode, inverse):
+    import torch
+    rng = np.random.default_rng(29)
+    comps = 2 if mode == "c2c" else 1
+    x = rng.standard_normal(shape + (comps,)).astype(np.float32)
+    oshape = shape[:-1] + (shape[-1] // 2 + 1, 2) if mode == "half" else shape + (2,)
+    rm = b200fft.REAL_HALF if mode == "half" else b200fft.REAL_FULL
+    plan = b200fft.plan_fft("float32", "float32", x.shape, oshape, inverse=inverse, real_mode=rm)
+    desc = plan.describe()
+    assert ("jitr2cplane" if mode == "half" else "jitplane") in desc.split("\n")[0] and "NVRTC" in desc, desc
+    assert plan.launches == len(shape) - 2
+    xt = torch.from_numpy(x).cuda()
+    out = torch.full(oshape, float("nan"), device="cuda")
+    b200fft.fft(out, xt, plan=plan)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float64)
+    got = got[..., 0] + 1j * got[..., 1]
+    xd = x.astype(np.float64)
+    xc = xd[..., 0] + (1j * xd[..., 1] if comps == 2 else 0)
+    axes = tuple(range(1, len(shape)))
+    want = np.fft.rfftn(xd[..., 0], axes=axes) if mode == "half" else (np.fft.ifftn(xc, axes=axes) if inverse else np.fft.fftn(xc, axes=axes))
+    assert np.isfinite(got).all()
+    assert np.linalg.norm(got - want) <= 2e-6 * np.sqrt(len(axes)) * np.linalg.norm(want), desc
+    plan.destroy()
