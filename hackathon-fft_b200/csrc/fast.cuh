@@ -261,6 +261,52 @@ __device__ __forceinline__ void run_stage(const Src& src, const Dst& dst, const 
   }
 }
 
+// One Stockham stage whose source and destination are the SAME shared-memory buffer: every butterfly of the tile is read
+// (and transformed) into registers first, the CTA synchronises, then everything is written back. Needs the whole stage in
+// registers — ROUNDS x R complex values per thread — which radix-8 stages of a 64 x 64 plane afford (2 x 8), and halves
+// the shared memory of a plane tile: 37 KB instead of 69 KB, six CTAs per SM instead of three.
+template <int R, int P, int N, int O, int CN, int NT, bool INV, class Src, class Dst>
+__device__ __forceinline__ void run_stage_inplace(const Src& src, const Dst& dst, const float2* __restrict__ tw) {
+  constexpr int NB = N / R;
+  constexpr int TOTAL = O * NB * CN;
+  constexpr int ROUNDS = (TOTAL + NT - 1) / NT;
+  static_assert(ROUNDS * R <= 64, "in-place stage: the tile does not fit the register file");
+  float2 x[ROUNDS][R];
+#pragma unroll
+  for (int it = 0; it < ROUNDS; ++it) {
+    const int q = (int)threadIdx.x + it * NT;
+    if (TOTAL % NT == 0 || q < TOTAL) {
+      const int c = (CN == 1) ? 0 : q % CN;
+      const int qn = (CN == 1) ? q : q / CN;
+      const int n = (O == 1) ? qn : qn % NB;
+      const int o = (O == 1) ? 0 : qn / NB;
+      const int p = (P == 1) ? 0 : n % P;
+#pragma unroll
+      for (int j = 0; j < R; ++j) x[it][j] = src.load(o, n + j * NB, c);
+      if constexpr (P > 1) {
+#pragma unroll
+        for (int j = 1; j < R; ++j) x[it][j] = cmulf(x[it][j], __ldg(tw + (j - 1) * P + p));
+      }
+      Dft<R, INV>::run(x[it]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < ROUNDS; ++it) {
+    const int q = (int)threadIdx.x + it * NT;
+    if (TOTAL % NT == 0 || q < TOTAL) {
+      const int c = (CN == 1) ? 0 : q % CN;
+      const int qn = (CN == 1) ? q : q / CN;
+      const int n = (O == 1) ? qn : qn % NB;
+      const int o = (O == 1) ? 0 : qn / NB;
+      const int p = (P == 1) ? 0 : n % P;
+      const int g = (P == 1) ? n : n / P;
+#pragma unroll
+      for (int k = 0; k < R; ++k) dst.store(o, g * (P * R) + p + k * P, c, x[it][k]);
+    }
+  }
+}
+
 // adapters: LayoutFor<Q, P> for a fixed tile shape
 template <int N>
 struct RowLayoutN {
@@ -360,6 +406,48 @@ __global__ void __launch_bounds__(NT) rows_kernel(const __grid_constant__ RowsAr
 template <int N, class RL, int C>
 constexpr size_t rows_smem_bytes() {
   return sizeof(float2) * (size_t)max_exchange_elems<RL, C, RowLayoutN<N>::template type>() * (RL::count > 2 ? 2 : 1);
+}
+
+// One LONG contiguous transform per CTA (8192 < N <= ~24000: two exchange buffers no longer fit shared memory): three stages
+// in ONE buffer, the middle stage exchanged in place through registers. (100, 16384) — the one published shape that
+// ran behind cuFFT as two split passes of ~11 us each — is a single launch of 100 CTAs this way.
+template <int N, class RL>
+constexpr size_t rows_ip_smem_bytes() {
+  int ex = 0;
+  for (int s = 0; s + 1 < RL::count; ++s) {  // RowLayout<N, Q, P>::size(1) of every exchange, the largest
+    const int P = RL::processed(s), Q = P * RL::r[s];
+    const int e = (P < 16 && Q % 2 == 0 && Q < N) ? N + (N / Q) * P : N;
+    ex = e > ex ? e : ex;
+  }
+  return sizeof(float2) * (size_t)ex;
+}
+// stages 1 .. count-2: shared -> registers -> barrier -> the same shared buffer in the next layout
+template <int N, class RL, int NT, bool INV, int S>
+__device__ __forceinline__ void rows_ip_middle(float2* buf, const float2* __restrict__ tw) {
+  if constexpr (S + 1 < RL::count) {
+    constexpr int P = RL::processed(S);
+    using Lin = RowLayout<N, P, P / RL::r[S - 1]>;
+    using Lout = RowLayout<N, P * RL::r[S], P>;
+    run_stage_inplace<RL::r[S], P, N, 1, 1, NT, INV>(SmemSrc<Lin>{buf}, SmemDst<Lout>{buf}, tw + RL::tw_offset(S));
+    __syncthreads();
+    rows_ip_middle<N, RL, NT, INV, S + 1>(buf, tw);
+  }
+}
+template <int N, class RL, int NT, bool INV>
+__global__ void __launch_bounds__(NT) rows_ip_kernel(const __grid_constant__ RowsArgs a) {
+  static_assert(RL::count >= 3 && RL::product() == N, "three or more stages that multiply to N");
+  extern __shared__ __align__(16) float2 smem_f2[];
+  pdl_wait();
+  const long long row = blockIdx.x;
+  constexpr int L = RL::count - 1;
+  using L0 = RowLayout<N, RL::r[0], 1>;
+  using LL = RowLayout<N, RL::processed(L), RL::processed(L - 1)>;
+  GlobalSrc<false> src{reinterpret_cast<const in_vec2*>(a.in) + row * N, N, 1, 1, 1};
+  run_stage<RL::r[0], 1, N, 1, 1, NT, INV>(src, SmemDst<L0>{smem_f2}, a.tw, 1.f, false);
+  __syncthreads();
+  rows_ip_middle<N, RL, NT, INV, 1>(smem_f2, a.tw);
+  GlobalDst dst{a.out + row * N, N, 1, 1, 1};
+  run_stage<RL::r[L], RL::processed(L), N, 1, 1, NT, INV>(SmemSrc<LL>{smem_f2}, dst, a.tw + RL::tw_offset(L), a.scale, a.do_scale != 0);
 }
 
 // strided axis, TMA-tiled: the tile [N][CW] is fetched by cp.async.bulk.tensor.3d box loads (tensor

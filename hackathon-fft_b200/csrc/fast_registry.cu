@@ -307,9 +307,11 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
     // TMA tiles need 16-byte global strides (even inner), complex fp32 source, a usable encoder
     const bool tma_ok = kind == COLS && src.comps == 2 && view.inner % 2 == 0 && tensor_map_encoder() != nullptr &&
                         (unsigned long long)view.inner * view.n * 8 < (1ull << 40);
+    const char* ip_env = std::getenv("B200FFT_ROWS_INPLACE");  // =0: long rows as two split passes again (A/B, tests)
+    const bool ip_ok = !(ip_env && ip_env[0] == '0');
     for (const Variant& v : registry()) {
-      const bool kind_ok = v.kind == kind || (v.kind == COLS_TMA && tma_ok);
-      if (kind_ok && v.n == (int)view.n && (v.full || (!p.desc.inverse && src.comps == 2)) &&
+      const bool kind_ok = (v.kind == kind || (v.kind == COLS_TMA && tma_ok)) && (ip_ok || !v.inv_ok);
+      if (kind_ok && v.n == (int)view.n && (v.full || (src.comps == 2 && (!p.desc.inverse || v.inv_ok))) &&
           can_group(ax.ordered, v.radices))
         cands.push_back(&v);
     }

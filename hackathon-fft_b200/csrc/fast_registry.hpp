@@ -29,6 +29,7 @@ struct Variant {
   int box_rows = 0;  // TMA box extent along the transform axis
   void (*launch_scatter)(bool, const ColsArgs&, const ScatterArgs&, unsigned, size_t, cudaStream_t) = nullptr;
   bool full;  // has inverse and real-input instantiations
+  bool inv_ok = false;  // not FULL, but complex inverse exists too (long in-place rows)
   // half-spectrum real transforms of length 2*n on top of this n-point row variant (FULL only)
   void (*launch_half)(bool c2r, const HalfArgs&, unsigned, cudaStream_t) = nullptr;
   cudaError_t (*prepare_half)() = nullptr;
@@ -102,6 +103,20 @@ struct RowsV {
       if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, false, VEC>, attr, (int)smem);
       if (!e) e = cudaFuncSetAttribute(rows_kernel<N, RL, C, NT, true, true>, attr, (int)smem);
     }
+    return e;
+  }
+};
+
+template <int N, class RL, int NT>
+struct RowsIpV {
+  static void launch(bool inv, bool, const RowsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    if (inv) rows_ip_kernel<N, RL, NT, true><<<grid, NT, smem, st>>>(a);
+    else rows_ip_kernel<N, RL, NT, false><<<grid, NT, smem, st>>>(a);
+  }
+  static cudaError_t prepare(size_t smem) {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, NT, false>, attr, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, NT, true>, attr, (int)smem);
     return e;
   }
 };
@@ -250,6 +265,22 @@ void reg_rows() {
 template <int N, int C, int NT, bool FULL, int... Rs>
 void reg_rows_v4() {
   reg_rows_impl<N, C, NT, FULL, true, Rs...>();
+}
+// one long row per CTA, three stages in one shared buffer (rows_ip_kernel): complex input, forward and inverse
+template <int N, int NT, int... Rs>
+void reg_rows_inplace() {
+  using RL = Radices<Rs...>;
+  static_assert(RL::product() == N, "radices must multiply to N");
+  Variant v;
+  v.kind = ROWS; v.n = N; v.radices = radix_vec<RL>(); v.tile = 1; v.threads = NT;
+  v.smem = rows_ip_smem_bytes<N, RL>();
+  v.name = "rowsIP" + std::to_string(N) + "_" + radix_name(v.radices) + "_c1_t" + std::to_string(NT);
+  v.launch_rows = &RowsIpV<N, RL, NT>::launch;
+  v.launch_cols = nullptr;
+  v.prepare = &RowsIpV<N, RL, NT>::prepare;
+  v.full = false;
+  v.inv_ok = true;
+  registry().push_back(v);
 }
 template <int N, int CW, int NT, bool FULL, int... Rs>
 void reg_cols() {

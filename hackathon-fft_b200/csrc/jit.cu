@@ -147,7 +147,8 @@ enum JitKind {
   JIT_SPLIT_B_ROWS, // rows_split_b_kernel<N2, RL, C, NT, INV>: the same for a contiguous axis
   // the two innermost axes in one in-place tile per (y, x) plane (plane.cuh); n = NY, n2 = NX (R2C: H), radices = y, radices2 = x
   JIT_PLANE_C2C,    // c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, INV, REAL>
-  JIT_PLANE_R2C     // r2c_plane_ip_kernel<NY, H, RLY, RLX, NT>
+  JIT_PLANE_R2C,    // r2c_plane_ip_kernel<NY, H, RLY, RLX, NT>
+  JIT_ROWS_IP       // rows_ip_kernel<N, RL, NT, INV>: one long row per CTA, three stages in ONE shared buffer (tile = 1)
 };
 
 struct JitSpec {
@@ -163,6 +164,7 @@ struct JitSpec {
 
   size_t esz() const { return f64 ? sizeof(double2) : sizeof(float2); }
   int tile_divides = 0;        // geometry only: the tile must divide this (split pass B rows never straddle transforms)
+  long long rows_hint = 0;     // geometry only: transforms per call when the planner knows it (few rows: more threads per row)
   bool plane() const { return kind == JIT_PLANE_C2C || kind == JIT_PLANE_R2C; }
   std::string plane_args() const {  // "<NY, NX, Radices<y...>, Radices<x...>"
     std::string ry, rx;
@@ -187,6 +189,8 @@ struct JitSpec {
       case JIT_PLANE_C2C: return "b200fft::c2c_plane_ip_kernel<" + plane_args() + ", " + std::to_string(threads) + ", " + inv + ", " + real + ">";
       case JIT_PLANE_R2C: return "b200fft::r2c_plane_ip_kernel<" + plane_args() + ", " + std::to_string(threads) + ">";
       case JIT_ROWS: return "b200fft::rows_kernel<" + head + ", " + inv + ", " + real + ">";
+      case JIT_ROWS_IP:
+        return "b200fft::rows_ip_kernel<" + std::to_string(n) + ", b200fft::Radices<" + radix_list() + ">, " + std::to_string(threads) + ", " + inv + ">";
       case JIT_COLS: return "b200fft::cols_kernel<" + head + ", " + inv + ", " + real + ">";
       case JIT_SCATTER: return "b200fft::cols_scatter_kernel<" + head + ", " + inv + ">";
       case JIT_R2C: return "b200fft::rows_r2c_kernel<" + head + ">";
@@ -207,6 +211,7 @@ struct JitSpec {
       case JIT_PLANE_R2C:
         return "b200fft::r2c_plane_ip_smem_bytes<" + std::to_string(n) + ", " + std::to_string(n2) + ", b200fft::Radices<" +
                std::to_string(radices2[0]) + ", " + std::to_string(radices2[1]) + ">>()";
+      case JIT_ROWS_IP: return "b200fft::rows_ip_smem_bytes<" + std::to_string(n) + ", b200fft::Radices<" + radix_list() + ">>()";
       case JIT_ROWS:
       case JIT_SPLIT_B_ROWS:
       case JIT_C2R_ODD:
@@ -222,7 +227,7 @@ struct JitSpec {
   }
   std::string name() const {
     static const char* const tag[] = {"jitrows", "jitcols", "jitscatter", "jitr2c", "jitr2creg", "jitr2codd", "jitc2r", "jitc2rodd",
-                                      "jitsplitA", "jitsplitBcols", "jitsplitBrows", "jitplane", "jitr2cplane"};
+                                      "jitsplitA", "jitsplitBcols", "jitsplitBrows", "jitplane", "jitr2cplane", "jitrowsIP"};
     if (plane())
       return std::string(tag[kind]) + std::to_string(n) + "x" + std::to_string(kind == JIT_PLANE_R2C ? 2 * n2 : n2) + "(" + radix_name(radices) +
              ";" + radix_name(radices2) + ")_inplace_t" + std::to_string(threads) + (f64 ? "_f64" : "");
@@ -244,6 +249,14 @@ struct JitSpec {
   size_t smem() const {
     if (plane()) return esz() * (size_t)n * (size_t)(n2 + n2 / radices2[0]);  // one buffer of NY rows, pitch NX + NX / r0
     long long P = 1, ex = 0;
+    if (kind == JIT_ROWS_IP) {  // rows_ip_smem_bytes: the largest exchange layout, once
+      for (size_t s = 0; s + 1 < radices.size(); ++s) {
+        const long long Q = P * radices[s];
+        ex = std::max(ex, (P < 16 && Q % 2 == 0 && Q < n) ? n + n / Q * P : (long long)n);
+        P = Q;
+      }
+      return esz() * (size_t)ex;
+    }
     for (size_t s = 0; s + 1 < radices.size(); ++s) {
       const long long Q = P * radices[s];
       long long elems;
@@ -582,6 +595,41 @@ bool jit_geometry(JitSpec* s, long long inner) {
   return s->smem() <= 227 * 1024;
 }
 
+// rows_ip_kernel (fast.cuh): one row per CTA; the in-place middle stage holds rounds * r1 points per thread in registers
+bool jit_rows_ip_geometry(JitSpec* s) {
+  if (s->radices.size() < 3 || s->radices.size() > 5 || s->real_in) return false;
+  const char* env = getenv("B200FFT_ROWS_INPLACE");
+  if (env && env[0] == '0') return false;
+  s->tile = 1;
+  double best = 1e30;
+  int best_nt = 0;
+  std::vector<int> order = s->radices, best_order;
+  std::sort(order.begin(), order.end());
+  do {  // the stage ORDER is free (same transform): one whose middle stages fit the register budget
+    for (int nt = 64; nt <= 512; nt += 32) {
+      const long long budget = std::min(64, (std::min(255, 65536 / nt) - 40) / 2);
+      long long held = 0;  // complex values a thread keeps across the barrier of an in-place stage
+      for (size_t i = 1; i + 1 < order.size(); ++i) held = std::max<long long>(held, ((long long)s->n / order[i] + nt - 1) / nt * order[i]);
+      if (held > budget) continue;
+      double waste = 0;
+      for (int r : order) {
+        const long long work = s->n / r, rounds = (work + nt - 1) / nt;
+        waste += (double)(rounds * nt - work) / (double)(rounds * nt);
+      }
+      // under two waves of CTAs the kernel is latency-bound: as many threads per row as the stages feed (10000 points,
+      // 100 rows: 0.0125 ms at 256 threads, 0.0105 at 512); otherwise 256, two or more CTAs per SM
+      const double want_nt = (s->rows_hint > 0 && s->rows_hint <= 2 * 148) ? 512.0 : 256.0;
+      double score = 4.0 * waste + 0.3 * std::fabs(std::log2((double)nt / want_nt)) + (held > 40 ? 0.5 : 0.0);
+      if (order != s->radices) score += 0.05;
+      if (score < best) { best = score; best_nt = nt; best_order = order; }
+    }
+  } while (std::next_permutation(order.begin(), order.end()));
+  if (!best_nt) return false;
+  s->threads = best_nt;
+  s->radices = best_order;
+  return s->smem() <= 200 * 1024;
+}
+
 // rows_r2c_reg_kernel's precondition (fast.cuh: r2c_reg_ok) apart from the tile, which jit_geometry picks
 bool r2c_reg_shape_ok(const JitSpec& s) {
   const int P = s.n / s.radices.back();
@@ -683,7 +731,7 @@ struct JitPass : Pass {
     return run(*k, spec, (outer + spec.tile - 1) / spec.tile, params, stream);
   }
   int launch_outer(const void* src, void* dst, int64_t outer, cudaStream_t stream) {
-    if (spec.kind == JIT_ROWS)
+    if (spec.kind == JIT_ROWS || spec.kind == JIT_ROWS_IP)
       return spec.f64 ? launch_rows<RowsArgs64, double2>(src, dst, outer, stream) : launch_rows<RowsArgs, float2>(src, dst, outer, stream);
     if (spec.kind == JIT_COLS) {
       void* params[1];
@@ -764,7 +812,8 @@ bool jit_enabled() {
 
 // kind + transform length + stage list for one axis; false when this tier does not serve it
 bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, bool inverse, HalfMode half, bool f64,
-                   JitSpec* spec) {
+                   JitSpec* spec, long long rows_hint = 0) {
+  spec->rows_hint = rows_hint;
   spec->inverse = inverse;
   spec->real_in = src.comps == 1;
   spec->f64 = f64;
@@ -798,6 +847,13 @@ bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, 
   // packed FADD2 adds: the measured win for mixed-radix and strided kernels, a loss for contiguous power-of-two rows
   // (dft.cuh, profiles/r1_packed_fadd2.md)
   spec->packed = !f64 && (spec->strided() || (spec->n & (spec->n - 1)) != 0);
+  // long contiguous rows: two exchange buffers leave one CTA per SM (4096 points, measured 2x slower) or do not fit at
+  // all (beyond ~14000); one buffer with the middle stage exchanged in place (profiles/r2_long_rows.md)
+  if (spec->kind == JIT_ROWS && (long long)spec->n * (long long)spec->esz() >= 32768) {
+    spec->kind = JIT_ROWS_IP;
+    if (jit_rows_ip_geometry(spec)) return true;
+    spec->kind = JIT_ROWS;
+  }
   if (!jit_geometry(spec, view.inner)) {
     if (spec->kind != JIT_R2C_REG) return false;
     spec->kind = JIT_R2C;  // no tile keeps whole warps per row group: the shared-memory unpack
@@ -972,7 +1028,9 @@ std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView
   if (!jit_enabled() || view.n < 2) return nullptr;
   const bool f64 = p.desc.out_dtype == B200FFT_F64;
   JitSpec spec;
-  if (view.n > 16384 || !jit_plan_axis(p.axes[axis], view, src, p.desc.inverse != 0, half, f64, &spec)) {
+  const long long rows = view.inner == 1 ? (long long)p.batch * view.outer_per_batch : 0;
+  if ((view.n > 16384 && view.inner != 1) || view.n > 32768 ||
+      !jit_plan_axis(p.axes[axis], view, src, p.desc.inverse != 0, half, f64, &spec, rows)) {
     // too long (or too many stages) for one tile: two passes, if the axis is a plain complex one
     if (half != HALF_NONE || view.n < 1024) return nullptr;
     return make_jit_split_pass(plan, axis, view, src, scale_inverse);
@@ -1011,8 +1069,9 @@ std::unique_ptr<Pass> make_jit_pass(b200fft_plan& plan, int axis, const AxisView
   std::string stages;
   for (uint32_t r : p.axes[axis].ordered) stages += (stages.empty() ? "" : ",") + std::to_string(r);
   char buf[400];
-  snprintf(buf, sizeof buf, "axis %d: %s n=%lld inner=%lld smem=%zuB regs=%d user stages=[%s] fused as %s(%s)%s [NVRTC, %.0f ms]", axis,
-           spec.name().c_str(), (long long)view.n, (long long)view.inner, pass->smem, k->regs, stages.c_str(),
+  snprintf(buf, sizeof buf, "axis %d: %s n=%lld inner=%lld smem=%zuB regs=%d%s user stages=[%s] fused as %s(%s)%s [NVRTC, %.0f ms]", axis,
+           spec.name().c_str(), (long long)view.n, (long long)view.inner, pass->smem, k->regs,
+           k->local_bytes ? (" local=" + std::to_string(k->local_bytes) + "B").c_str() : "", stages.c_str(),
            need_tw2 ? "(2)" : "", radix_name(spec.radices).c_str(),
            half == HALF_R2C ? (spec.kind == JIT_R2C_ODD ? " r2c (real rows, bins 0..n/2 stored)" : " r2c")
            : half == HALF_C2R ? (spec.kind == JIT_C2R_ODD ? " c2r (Hermitian-extended load)" : " c2r") : spec.real_in ? " real-in" : "",

@@ -113,52 +113,6 @@ constexpr size_t c2c_plane_smem_bytes() {
   return sizeof(float2) * (size_t)(NY * (NX + 8) + c2c_plane_exchange_elems<NY, NX, RLY, RLX>());
 }
 
-// One Stockham stage whose source and destination are the SAME shared-memory buffer: every butterfly of the tile is read
-// (and transformed) into registers first, the CTA synchronises, then everything is written back. Needs the whole stage in
-// registers — ROUNDS x R complex values per thread — which radix-8 stages of a 64 x 64 plane afford (2 x 8), and halves
-// the shared memory of a plane tile: 37 KB instead of 69 KB, six CTAs per SM instead of three.
-template <int R, int P, int N, int O, int CN, int NT, bool INV, class Src, class Dst>
-__device__ __forceinline__ void run_stage_inplace(const Src& src, const Dst& dst, const float2* __restrict__ tw) {
-  constexpr int NB = N / R;
-  constexpr int TOTAL = O * NB * CN;
-  constexpr int ROUNDS = (TOTAL + NT - 1) / NT;
-  static_assert(ROUNDS * R <= 40, "in-place stage: the tile does not fit the register file");
-  float2 x[ROUNDS][R];
-#pragma unroll
-  for (int it = 0; it < ROUNDS; ++it) {
-    const int q = (int)threadIdx.x + it * NT;
-    if (TOTAL % NT == 0 || q < TOTAL) {
-      const int c = (CN == 1) ? 0 : q % CN;
-      const int qn = (CN == 1) ? q : q / CN;
-      const int n = (O == 1) ? qn : qn % NB;
-      const int o = (O == 1) ? 0 : qn / NB;
-      const int p = (P == 1) ? 0 : n % P;
-#pragma unroll
-      for (int j = 0; j < R; ++j) x[it][j] = src.load(o, n + j * NB, c);
-      if constexpr (P > 1) {
-#pragma unroll
-        for (int j = 1; j < R; ++j) x[it][j] = cmulf(x[it][j], __ldg(tw + (j - 1) * P + p));
-      }
-      Dft<R, INV>::run(x[it]);
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int it = 0; it < ROUNDS; ++it) {
-    const int q = (int)threadIdx.x + it * NT;
-    if (TOTAL % NT == 0 || q < TOTAL) {
-      const int c = (CN == 1) ? 0 : q % CN;
-      const int qn = (CN == 1) ? q : q / CN;
-      const int n = (O == 1) ? qn : qn % NB;
-      const int o = (O == 1) ? 0 : qn / NB;
-      const int p = (P == 1) ? 0 : n % P;
-      const int g = (P == 1) ? n : n / P;
-#pragma unroll
-      for (int k = 0; k < R; ++k) dst.store(o, g * (P * R) + p + k * P, c, x[it][k]);
-    }
-  }
-}
-
 // rows of NI points, one pad element after every Q = first x radix (the RowLayout padding of the first stage: the scatter
 // of butterfly n to Q n + k lands on (Q + 1) n + k, distinct banks), pitch NI + NI / Q
 template <int NI, int Q>

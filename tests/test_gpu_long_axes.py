@@ -31,10 +31,22 @@ def _run(shape, inverse=False, bases=None):
 
 
 @pytest.mark.parametrize("shape,inverse", [((3, 16384), False), ((2, 16384), True), ((100, 16384), False)])
-def test_contiguous_long_axis(shape, inverse):
+def test_contiguous_long_axis(shape, inverse, monkeypatch):
+    monkeypatch.setenv("B200FFT_ROWS_INPLACE", "0")
     rel, mx, desc = _run(shape, inverse)
     assert "split n=16384 = 128 x 128" in desc and "splitB_rows128" in desc, desc
     assert rel < 2e-6 and mx < 1e-5, (rel, mx)
+
+
+@pytest.mark.parametrize("shape,inverse", [((3, 16384), False), ((2, 16384), True), ((100, 16384), False), ((149, 16384), True)])
+def test_long_row_in_one_launch(shape, inverse):
+    """16384 points do not fit two exchange buffers; rows_ip_kernel (csrc/fast.cuh) keeps ONE and exchanges the middle stage
+    in place through registers, so the published (100, 16384) shape is one launch instead of two split passes."""
+    rel, mx, desc = _run(shape, inverse)
+    assert desc.strip().count("\n") == 0 and "rowsIP16384_32x32x16_c1_t512" in desc, desc
+    assert rel < 2e-6 and mx < 1e-5, (rel, mx)
+    rel2, _, desc2 = _run(shape, inverse, bases=[[4]])   # user bases that regroup into (32, 32, 16)? 4^7: no -> other tiers
+    assert rel2 < 2e-6, desc2
 
 
 @pytest.mark.parametrize("shape,inverse", [((2, 1920, 1080), False), ((1, 1920, 1080), True),
@@ -63,7 +75,49 @@ def test_split_respects_user_bases():
     assert "split n=1920 = 128 x 15" in desc and rel < 2e-6, desc
 
 
-@pytest.mark.parametrize("shape,inverse", [((3, 20000), False), ((2, 100000), True), ((1, 1 << 18), False), ((1, 1 << 20), False),
+@pytest.mark.parametrize("shape,inverse,dtype", [((3, 20000), False, "float32"), ((5, 10000), True, "float32"), ((150, 5000), False, "float32"),
+                                                 ((3, 8640), True, "float32"), ((2, 15625), False, "float32"), ((3, 10000), False, "float64"),
+                                                 ((4, 4096), True, "float64"), ((2, 12288), False, "float32")])
+def test_long_rows_specialised_in_place(shape, inverse, dtype):
+    """Contiguous rows of 4096 .. ~25000 points without a registered variant: rows_ip_kernel specialised at plan time
+    (csrc/jit.cu, JIT_ROWS_IP) — any stage count from 3 to 5, the stage order chosen so the in-place stages fit the
+    register file. One launch; B200FFT_ROWS_INPLACE=0 gives the two-buffer / two-pass plan back."""
+    import torch
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal(shape + (2,)).astype(dtype)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.full_like(d_in, float("nan"))
+    plan = b200fft.plan_fft(dtype, dtype, d_in.shape, d_in.shape, inverse=inverse)
+    desc = plan.describe()
+    assert "jitrowsIP%d_" % shape[1] in desc and desc.strip().count("\n") == 0 and "local=" not in desc, desc
+    b200fft.fft(d_out, d_in, plan=plan)
+    torch.cuda.synchronize()
+    plan.destroy()
+    xc = x[..., 0].astype(np.float64) + 1j * x[..., 1]
+    want = np.fft.ifft(xc, axis=1) if inverse else np.fft.fft(xc, axis=1)
+    got = d_out.cpu().numpy().astype(np.float64)
+    rel = np.linalg.norm((got[..., 0] + 1j * got[..., 1]) - want) / np.linalg.norm(want)
+    assert rel < (1e-14 if dtype == "float64" else 2.5e-6), (rel, desc)
+
+
+def test_long_rows_cast_on_load():
+    """uint8 complex input straight into the in-place row kernel (the reference's own input type, fft/tests/fft.mojo:96-104)."""
+    import torch
+    rng = np.random.default_rng(19)
+    x = rng.integers(0, 256, size=(6, 6000, 2), dtype=np.uint8)
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.empty((6, 6000, 2), dtype=torch.float32, device="cuda")
+    plan = b200fft.plan_fft("uint8", "float32", d_in.shape, d_out.shape)
+    assert "jitrowsIP6000_" in plan.describe() and "_inu8" in plan.describe(), plan.describe()
+    b200fft.fft(d_out, d_in, plan=plan)
+    torch.cuda.synchronize()
+    plan.destroy()
+    want = np.fft.fft(x[..., 0].astype(np.float64) + 1j * x[..., 1], axis=1)
+    got = d_out.cpu().numpy().astype(np.float64)
+    assert np.linalg.norm((got[..., 0] + 1j * got[..., 1]) - want) / np.linalg.norm(want) < 2e-6
+
+
+@pytest.mark.parametrize("shape,inverse", [((3, 30000), False), ((2, 100000), True), ((1, 1 << 18), False), ((1, 1 << 20), False),
                                            ((2, 20000, 6), False), ((2, 3, 30000), True), ((1, 5 ** 7), False)])
 def test_long_axes_without_a_registered_split(shape, inverse):
     """Any long axis whose stage list splits into two tile-sized halves: both passes specialised at plan time
@@ -74,13 +128,15 @@ def test_long_axes_without_a_registered_split(shape, inverse):
     assert rel < 2.5e-6 and mx < 1e-5, (rel, mx, desc)
 
 
-def test_long_axis_fp64():
+@pytest.mark.parametrize("n", [10000, 40000])
+def test_long_axis_fp64(n):
     import torch
     rng = np.random.default_rng(3)
-    x = rng.standard_normal((2, 10000, 2))
+    x = rng.standard_normal((2, n, 2))
     plan = b200fft.plan_fft("float64", "float64", x.shape, x.shape)
     desc = plan.describe()
-    assert "split n=10000" in desc and "_f64" in desc, desc
+    # 10000 points: one in-place tile (160 KB); 40000: 640 KB per row, two passes
+    assert ("jitrowsIP10000" if n == 10000 else "split n=40000") in desc and "_f64" in desc, desc
     out = torch.full(x.shape, float("nan"), device="cuda", dtype=torch.float64)
     b200fft.fft(out, torch.from_numpy(x).cuda(), plan=plan)
     torch.cuda.synchronize()
