@@ -411,43 +411,47 @@ constexpr size_t rows_smem_bytes() {
 // One LONG contiguous transform per CTA (8192 < N <= ~24000: two exchange buffers no longer fit shared memory): three stages
 // in ONE buffer, the middle stage exchanged in place through registers. (100, 16384) — the one published shape that
 // ran behind cuFFT as two split passes of ~11 us each — is a single launch of 100 CTAs this way.
-template <int N, class RL>
+template <int N, class RL, int C = 1>
 constexpr size_t rows_ip_smem_bytes() {
   int ex = 0;
-  for (int s = 0; s + 1 < RL::count; ++s) {  // RowLayout<N, Q, P>::size(1) of every exchange, the largest
+  for (int s = 0; s + 1 < RL::count; ++s) {  // RowLayout<N, Q, P>::size(C) of every exchange, the largest
     const int P = RL::processed(s), Q = P * RL::r[s];
     const int e = (P < 16 && Q % 2 == 0 && Q < N) ? N + (N / Q) * P : N;
     ex = e > ex ? e : ex;
   }
-  return sizeof(float2) * (size_t)ex;
+  return sizeof(float2) * (size_t)ex * C;
 }
 // stages 1 .. count-2: shared -> registers -> barrier -> the same shared buffer in the next layout
-template <int N, class RL, int NT, bool INV, int S>
+template <int N, class RL, int C, int NT, bool INV, int S>
 __device__ __forceinline__ void rows_ip_middle(float2* buf, const float2* __restrict__ tw) {
   if constexpr (S + 1 < RL::count) {
     constexpr int P = RL::processed(S);
     using Lin = RowLayout<N, P, P / RL::r[S - 1]>;
     using Lout = RowLayout<N, P * RL::r[S], P>;
-    run_stage_inplace<RL::r[S], P, N, 1, 1, NT, INV>(SmemSrc<Lin>{buf}, SmemDst<Lout>{buf}, tw + RL::tw_offset(S));
+    run_stage_inplace<RL::r[S], P, N, C, 1, NT, INV>(SmemSrc<Lin>{buf}, SmemDst<Lout>{buf}, tw + RL::tw_offset(S));
     __syncthreads();
-    rows_ip_middle<N, RL, NT, INV, S + 1>(buf, tw);
+    rows_ip_middle<N, RL, C, NT, INV, S + 1>(buf, tw);
   }
 }
-template <int N, class RL, int NT, bool INV>
+template <int N, class RL, int C, int NT, bool INV, bool REAL = false>
 __global__ void __launch_bounds__(NT) rows_ip_kernel(const __grid_constant__ RowsArgs a) {
   static_assert(RL::count >= 3 && RL::product() == N, "three or more stages that multiply to N");
   extern __shared__ __align__(16) float2 smem_f2[];
   pdl_wait();
-  const long long row = blockIdx.x;
+  const long long row0 = (long long)blockIdx.x * C;
+  // one row per CTA: the grid is the row count, no ragged tile, and the accessors' bounds checks fold away
+  const int valid = C == 1 ? 1 : (int)min((long long)C, a.nrows - row0);
   constexpr int L = RL::count - 1;
   using L0 = RowLayout<N, RL::r[0], 1>;
   using LL = RowLayout<N, RL::processed(L), RL::processed(L - 1)>;
-  GlobalSrc<false> src{reinterpret_cast<const in_vec2*>(a.in) + row * N, N, 1, 1, 1};
-  run_stage<RL::r[0], 1, N, 1, 1, NT, INV>(src, SmemDst<L0>{smem_f2}, a.tw, 1.f, false);
+  const void* in = REAL ? (const void*)(reinterpret_cast<const in_scalar*>(a.in) + row0 * N)
+                        : (const void*)(reinterpret_cast<const in_vec2*>(a.in) + row0 * N);
+  GlobalSrc<REAL> src{in, N, 1, valid, 1};
+  run_stage<RL::r[0], 1, N, C, 1, NT, INV>(src, SmemDst<L0>{smem_f2}, a.tw, 1.f, false);
   __syncthreads();
-  rows_ip_middle<N, RL, NT, INV, 1>(smem_f2, a.tw);
-  GlobalDst dst{a.out + row * N, N, 1, 1, 1};
-  run_stage<RL::r[L], RL::processed(L), N, 1, 1, NT, INV>(SmemSrc<LL>{smem_f2}, dst, a.tw + RL::tw_offset(L), a.scale, a.do_scale != 0);
+  rows_ip_middle<N, RL, C, NT, INV, 1>(smem_f2, a.tw);
+  GlobalDst dst{a.out + row0 * N, N, 1, valid, 1};
+  run_stage<RL::r[L], RL::processed(L), N, C, 1, NT, INV>(SmemSrc<LL>{smem_f2}, dst, a.tw + RL::tw_offset(L), a.scale, a.do_scale != 0);
 }
 
 // strided axis, TMA-tiled: the tile [N][CW] is fetched by cp.async.bulk.tensor.3d box loads (tensor

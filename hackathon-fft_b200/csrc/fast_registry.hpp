@@ -110,13 +110,13 @@ struct RowsV {
 template <int N, class RL, int NT>
 struct RowsIpV {
   static void launch(bool inv, bool, const RowsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
-    if (inv) rows_ip_kernel<N, RL, NT, true><<<grid, NT, smem, st>>>(a);
-    else rows_ip_kernel<N, RL, NT, false><<<grid, NT, smem, st>>>(a);
+    if (inv) rows_ip_kernel<N, RL, 1, NT, true><<<grid, NT, smem, st>>>(a);
+    else rows_ip_kernel<N, RL, 1, NT, false><<<grid, NT, smem, st>>>(a);
   }
   static cudaError_t prepare(size_t smem) {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    cudaError_t e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, NT, false>, attr, (int)smem);
-    if (!e) e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, NT, true>, attr, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, 1, NT, false>, attr, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, 1, NT, true>, attr, (int)smem);
     return e;
   }
 };

@@ -148,7 +148,7 @@ enum JitKind {
   // the two innermost axes in one in-place tile per (y, x) plane (plane.cuh); n = NY, n2 = NX (R2C: H), radices = y, radices2 = x
   JIT_PLANE_C2C,    // c2c_plane_ip_kernel<NY, NX, RLY, RLX, NT, INV, REAL>
   JIT_PLANE_R2C,    // r2c_plane_ip_kernel<NY, H, RLY, RLX, NT>
-  JIT_ROWS_IP       // rows_ip_kernel<N, RL, NT, INV>: one long row per CTA, three stages in ONE shared buffer (tile = 1)
+  JIT_ROWS_IP       // rows_ip_kernel<N, RL, C, NT, INV, REAL>: `tile` rows per CTA, 3-5 stages in ONE shared buffer
 };
 
 struct JitSpec {
@@ -190,7 +190,7 @@ struct JitSpec {
       case JIT_PLANE_R2C: return "b200fft::r2c_plane_ip_kernel<" + plane_args() + ", " + std::to_string(threads) + ">";
       case JIT_ROWS: return "b200fft::rows_kernel<" + head + ", " + inv + ", " + real + ">";
       case JIT_ROWS_IP:
-        return "b200fft::rows_ip_kernel<" + std::to_string(n) + ", b200fft::Radices<" + radix_list() + ">, " + std::to_string(threads) + ", " + inv + ">";
+        return "b200fft::rows_ip_kernel<" + head + ", " + inv + ", " + real + ">";
       case JIT_COLS: return "b200fft::cols_kernel<" + head + ", " + inv + ", " + real + ">";
       case JIT_SCATTER: return "b200fft::cols_scatter_kernel<" + head + ", " + inv + ">";
       case JIT_R2C: return "b200fft::rows_r2c_kernel<" + head + ">";
@@ -211,7 +211,7 @@ struct JitSpec {
       case JIT_PLANE_R2C:
         return "b200fft::r2c_plane_ip_smem_bytes<" + std::to_string(n) + ", " + std::to_string(n2) + ", b200fft::Radices<" +
                std::to_string(radices2[0]) + ", " + std::to_string(radices2[1]) + ">>()";
-      case JIT_ROWS_IP: return "b200fft::rows_ip_smem_bytes<" + std::to_string(n) + ", b200fft::Radices<" + radix_list() + ">>()";
+      case JIT_ROWS_IP: return "b200fft::rows_ip_smem_bytes<" + shape_args() + ">()";
       case JIT_ROWS:
       case JIT_SPLIT_B_ROWS:
       case JIT_C2R_ODD:
@@ -255,7 +255,7 @@ struct JitSpec {
         ex = std::max(ex, (P < 16 && Q % 2 == 0 && Q < n) ? n + n / Q * P : (long long)n);
         P = Q;
       }
-      return esz() * (size_t)ex;
+      return esz() * (size_t)ex * (size_t)tile;
     }
     for (size_t s = 0; s + 1 < radices.size(); ++s) {
       const long long Q = P * radices[s];
@@ -597,35 +597,42 @@ bool jit_geometry(JitSpec* s, long long inner) {
 
 // rows_ip_kernel (fast.cuh): one row per CTA; the in-place middle stage holds rounds * r1 points per thread in registers
 bool jit_rows_ip_geometry(JitSpec* s) {
-  if (s->radices.size() < 3 || s->radices.size() > 5 || s->real_in) return false;
+  if (s->radices.size() < 3 || s->radices.size() > 5) return false;
   const char* env = getenv("B200FFT_ROWS_INPLACE");
   if (env && env[0] == '0') return false;
-  s->tile = 1;
   double best = 1e30;
-  int best_nt = 0;
+  int best_nt = 0, best_tile = 0;
   std::vector<int> order = s->radices, best_order;
   std::sort(order.begin(), order.end());
+  const bool few_rows = s->rows_hint > 0 && s->rows_hint <= 2 * 148;
   do {  // the stage ORDER is free (same transform): one whose middle stages fit the register budget
-    for (int nt = 64; nt <= 512; nt += 32) {
-      const long long budget = std::min(64, (std::min(255, 65536 / nt) - 40) / 2);
-      long long held = 0;  // complex values a thread keeps across the barrier of an in-place stage
-      for (size_t i = 1; i + 1 < order.size(); ++i) held = std::max<long long>(held, ((long long)s->n / order[i] + nt - 1) / nt * order[i]);
-      if (held > budget) continue;
-      double waste = 0;
-      for (int r : order) {
-        const long long work = s->n / r, rounds = (work + nt - 1) / nt;
-        waste += (double)(rounds * nt - work) / (double)(rounds * nt);
+    // one row per CTA: two or three rows per CTA measured no better (11986 x 2187: 0.078 ms at c1 t128, 0.088 at c2 t192;
+    // 10485 x 2500: 0.078 vs 0.087), and rows short enough to need it stay on the two-buffer tile (jit_plan_axis)
+    for (int tile : {1}) {
+      for (int nt = 96; nt <= 512; nt += 32) {
+        const long long budget = std::min(64, (std::min(255, 65536 / nt) - 40) / 2);
+        long long held = 0;  // complex values a thread keeps across the barrier of an in-place stage
+        for (size_t i = 1; i + 1 < order.size(); ++i)
+          held = std::max<long long>(held, ((long long)tile * s->n / order[i] + nt - 1) / nt * order[i]);
+        if (held > budget) continue;
+        double waste = 0;
+        for (int r : order) {
+          const long long work = (long long)tile * s->n / r, rounds = (work + nt - 1) / nt;
+          waste += (double)(rounds * nt - work) / (double)(rounds * nt);
+        }
+        // under two waves of CTAs the kernel is latency-bound: as many threads per row as the stages feed (10000 points,
+        // 100 rows: 0.0125 ms at 256 threads, 0.0105 at 512); 64-thread CTAs run out of CTA slots (14563 x 1800: 0.111 ms)
+        const double want_nt = few_rows ? 512.0 : 256.0;
+        double score = 4.0 * waste + 0.3 * std::fabs(std::log2((double)nt / want_nt)) + (held > 40 ? 0.5 : 0.0);
+        // a permuted order only when the given one does not fit (8738 x 3000: 20x15x10 0.083 ms, 10x20x15 0.128)
+        if (order != s->radices) score += 1.0;
+        if (score < best) { best = score; best_nt = nt; best_order = order; best_tile = tile; }
       }
-      // under two waves of CTAs the kernel is latency-bound: as many threads per row as the stages feed (10000 points,
-      // 100 rows: 0.0125 ms at 256 threads, 0.0105 at 512); otherwise 256, two or more CTAs per SM
-      const double want_nt = (s->rows_hint > 0 && s->rows_hint <= 2 * 148) ? 512.0 : 256.0;
-      double score = 4.0 * waste + 0.3 * std::fabs(std::log2((double)nt / want_nt)) + (held > 40 ? 0.5 : 0.0);
-      if (order != s->radices) score += 0.05;
-      if (score < best) { best = score; best_nt = nt; best_order = order; }
     }
   } while (std::next_permutation(order.begin(), order.end()));
   if (!best_nt) return false;
   s->threads = best_nt;
+  s->tile = best_tile;
   s->radices = best_order;
   return s->smem() <= 200 * 1024;
 }
@@ -849,7 +856,30 @@ bool jit_plan_axis(const AxisSpec& ax, const AxisView& view, const IoSpec& src, 
   spec->packed = !f64 && (spec->strided() || (spec->n & (spec->n - 1)) != 0);
   // long contiguous rows: two exchange buffers leave one CTA per SM (4096 points, measured 2x slower) or do not fit at
   // all (beyond ~14000); one buffer with the middle stage exchanged in place (profiles/r2_long_rows.md)
-  if (spec->kind == JIT_ROWS && (long long)spec->n * (long long)spec->esz() >= 32768) {
+  static const long long ip_min_bytes = [] {
+    const char* e = getenv("B200FFT_ROWS_INPLACE_MIN");  // row bytes from which the one-buffer kernel is tried
+    return e ? atoll(e) : 16384LL;
+  }();
+  // every 3+-stage row from 2048 points gains at large batch (11986 x 2187: 0.126 -> 0.078 ms, 8738 x 3000: 0.113 -> 0.083;
+  // 14563 x 1800 does not: 0.091 -> 0.092); under two waves of CTAs the short ones are a wash or lose a little
+  // (100 x 3600: 0.0064 -> 0.0075), so those keep the two-buffer tile
+  const long long row_bytes = (long long)spec->n * (long long)spec->esz();
+  const bool few_rows = rows_hint > 0 && rows_hint <= 2 * 148;
+  // two wide stages containing a radix-40 / 50 codelet lose to three narrow stages in one buffer (26214 x 1000: 40x25
+  // 0.097 ms, 10x10x10 in place 0.082; 13107 x 2000: 50x40 0.104, 20x10x10 0.084; 40x40, 36x36 and 48x32 do not)
+  if (spec->kind == JIT_ROWS && !f64 && !few_rows && spec->n >= 1000 && spec->radices.size() == 2 && !getenv("B200FFT_JIT_MAX_RADIX")) {
+    const int n40 = (int)std::count(spec->radices.begin(), spec->radices.end(), 40);
+    const int n50 = (int)std::count(spec->radices.begin(), spec->radices.end(), 50);
+    JitSpec narrow = *spec;
+    if ((n50 > 0 || n40 == 1) && jit_group_cap(ax.ordered, JIT_MAX_RADIX, &narrow.radices) && narrow.radices.size() == 3) {
+      narrow.kind = JIT_ROWS_IP;
+      if (jit_rows_ip_geometry(&narrow)) {
+        *spec = narrow;
+        return true;
+      }
+    }
+  }
+  if (spec->kind == JIT_ROWS && row_bytes >= ip_min_bytes && (row_bytes >= 32768 || !few_rows)) {
     spec->kind = JIT_ROWS_IP;
     if (jit_rows_ip_geometry(spec)) return true;
     spec->kind = JIT_ROWS;

@@ -276,7 +276,10 @@ def test_mgpu_needs_cuda_no_fallback():
 def test_jit_sources_compile_with_nvrtc_for_sm100a():
     """The plan-time specialisation tier's sources (the device headers embedded in the library) compile for sm_100a
     with NVRTC in this container: rows and strided kernels, forward / inverse, real input, a prime radix above 32."""
-    for kw, want in ((dict(n=1000), "rows_kernel<1000, b200fft::Radices<40, 25>"),      # wide codelets save a stage
+    for kw, want in ((dict(n=1000), "rows_ip_kernel<1000, b200fft::Radices<10, 10, 10>"),  # three narrow stages in one buffer beat 40 x 25
+                     (dict(n=1296), "rows_kernel<1296, b200fft::Radices<36, 36>"),      # wide codelets save a stage
+                     (dict(n=16384, inverse=True), "rows_ip_kernel<16384, b200fft::Radices<32, 32, 16>, 1, 512, true, false>"),
+                     (dict(n=10000, in_dtype="float64", out_dtype="float64"), "rows_ip_kernel<10000, b200fft::Radices<10, 10, 10, 10>"),
                      (dict(n=1000, half=1), "rows_r2c_kernel<500, b200fft::Radices<25, 20>"),
                      (dict(n=1000, half=2), "rows_c2r_kernel<500, b200fft::Radices<25, 20>"),
                      (dict(n=243, half=1), "rows_r2c_odd_kernel<243, b200fft::Radices<27, 9>"),
