@@ -100,6 +100,28 @@ def test_long_rows_specialised_in_place(shape, inverse, dtype):
     assert rel < (1e-14 if dtype == "float64" else 2.5e-6), (rel, desc)
 
 
+@pytest.mark.parametrize("n,dtype", [(3000, "float32"), (6000, "uint8"), (10000, "float64")])
+def test_long_rows_real_input_full_spectrum(n, dtype):
+    """Real input, full spectrum out (the reference's default mode): the one-buffer kernel's REAL instantiation reads the
+    scalar array and casts on load."""
+    import torch
+    rng = np.random.default_rng(23)
+    x = rng.integers(0, 256, size=(301, n, 1)).astype(dtype) if dtype == "uint8" else rng.standard_normal((301, n, 1)).astype(dtype)
+    odt = "float64" if dtype == "float64" else "float32"
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.full((301, n, 2), float("nan"), dtype=getattr(torch, odt), device="cuda")
+    plan = b200fft.plan_fft(dtype, odt, d_in.shape, d_out.shape)
+    desc = plan.describe()
+    assert "jitrowsIP%d_" % n in desc and "real-in" in desc, desc
+    b200fft.fft(d_out, d_in, plan=plan)
+    torch.cuda.synchronize()
+    plan.destroy()
+    want = np.fft.fft(x[..., 0].astype(np.float64), axis=1)
+    got = d_out.cpu().numpy().astype(np.float64)
+    rel = np.linalg.norm((got[..., 0] + 1j * got[..., 1]) - want) / np.linalg.norm(want)
+    assert rel < (1e-14 if odt == "float64" else 2.5e-6), (rel, desc)
+
+
 def test_long_rows_cast_on_load():
     """uint8 complex input straight into the in-place row kernel (the reference's own input type, fft/tests/fft.mojo:96-104)."""
     import torch
