@@ -48,13 +48,18 @@ KERNELS = [
     ("c2r_plane64x64", r"c2r_plane_kernel<64, 32, b200fft::Radices<8, 8>, b200fft::Radices<8, 4>, 128>"),
     ("c2c_plane128x128_inplace_fwd", r"c2c_plane_ip_kernel<128, 128, b200fft::Radices<16, 8>, b200fft::Radices<16, 8>, 512, false, false>"),
     ("r2c_plane128x128_inplace", r"r2c_plane_ip_kernel<128, 64, b200fft::Radices<8, 16>, b200fft::Radices<8, 8>, 512>"),
+    # one-buffer row kernel (rows_ip_kernel, csrc/fast.cuh)
+    ("rows_ip16384_32x32x16_fwd", r"rows_ip_kernel<16384, b200fft::Radices<32, 32, 16>, 1, 512, false, false>"),
+    ("rows_ip4096_16x16x16_fwd", r"rows_ip_kernel<4096, b200fft::Radices<16, 16, 16>, 1, 256, false, false>"),
 ]
 MAX_LINES = 6000  # longer listings (the runtime-length kernel unrolls 31 codelets: 25 MB) are cut here; the histogram counts all of it
 
 # plan-time specialised kernels (csrc/jit.cu): compiled here with NVRTC through b200fft_jit_probe (no GPU needed), the
 # cubins kept by B200FFT_JIT_DUMP_DIR. (file name, probe arguments)
 JIT_KERNELS = [
-    ("jit_rows1000_40x25_fwd", dict(n=1000)),
+    ("jit_rows_ip1000_10x10x10_fwd", dict(n=1000)),
+    ("jit_rows1296_36x36_fwd", dict(n=1296)),
+    ("jit_rows_ip20000_20x40x25_fwd", dict(n=20000)),
     ("jit_cols1000_40x25_fwd", dict(n=1000, inner=1000)),
     ("jit_rows100_10x10_fwd", dict(n=100)),
     ("jit_r2c500_25x20", dict(n=1000, half=1)),
