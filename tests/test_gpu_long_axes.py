@@ -75,6 +75,27 @@ def test_split_respects_user_bases():
     assert "split n=1920 = 128 x 15" in desc and rel < 2e-6, desc
 
 
+@pytest.mark.parametrize("n", [2048, 2160, 4096, 4320, 8192])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_registered_one_buffer_rows(n, inverse):
+    """The registered one-buffer variants (fast_reg_rows_*.cu: reg_rows_inplace) serve complex input in both directions;
+    real input of the same lengths stays on the two-buffer variants."""
+    rel, mx, desc = _run((301, n), inverse)
+    assert "rowsIP%d_" % n in desc and desc.strip().count("\n") == 0, desc
+    assert rel < 2e-6 and mx < 1e-5, (rel, mx)
+    import torch
+    x = torch.randn(5, n, 1, device="cuda")
+    out = torch.empty(5, n, 2, device="cuda")
+    plan = b200fft.plan_fft("float32", "float32", x.shape, out.shape)
+    assert "generic" not in plan.describe(), plan.describe()
+    b200fft.fft(out, x, plan=plan)
+    torch.cuda.synchronize()
+    plan.destroy()
+    want = torch.fft.fft(x[..., 0].double())
+    got = torch.view_as_complex(out.double().contiguous())
+    assert float((got - want).norm() / want.norm()) < 2e-6
+
+
 @pytest.mark.parametrize("shape,inverse,dtype", [((3, 20000), False, "float32"), ((5, 10000), True, "float32"), ((150, 5000), False, "float32"),
                                                  ((3, 8640), True, "float32"), ((2, 15625), False, "float32"), ((3, 10000), False, "float64"),
                                                  ((4, 4096), True, "float64"), ((2, 12288), False, "float32")])
