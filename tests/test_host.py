@@ -297,6 +297,26 @@ def test_jit_sources_compile_with_nvrtc_for_sm100a():
     assert e.value.status == 3
 
 
+def test_row_planner_one_buffer_rules(monkeypatch):
+    """Which contiguous rows the plan-time tier gives to the one-buffer kernel (csrc/jit.cu: jit_plan_axis,
+    jit_rows_ip_geometry; measured in profiles/r2_long_rows.md). Host-only: the planner + an NVRTC compile."""
+    def kernel(n, **kw):
+        return b200fft.jit_probe(n, **kw).split(":")[0]
+    assert kernel(1800).startswith("jitrows1800_")            # under 16 KB per row: two buffers, several rows per CTA
+    assert kernel(2187) == "jitrowsIP2187_27x9x9_c1_t128"     # 3 stages from 2048 points: one buffer, one row per CTA
+    assert kernel(1536) == "jitrows1536_48x32_c3_t96"         # two wide stages that measured faster stay
+    assert kernel(2000) == "jitrowsIP2000_20x10x10_c1_t128"   # ... a radix-40/50 codelet does not (50 x 40)
+    assert kernel(20000) == "jitrowsIP20000_20x40x25_c1_t512"  # order permuted: 25 in the middle would hold 50 values at 512 threads
+    assert kernel(3000) == "jitrowsIP3000_20x15x10_c1_t160"   # ... and is left alone when it fits
+    assert kernel(1024, in_dtype="float64", out_dtype="float64").startswith("jitrowsIP1024_16x8x8_c1_t128_f64")  # the rule is in bytes
+    with pytest.raises(b200fft.B200FFTError):                  # no stage order fits the register budget: two passes
+        b200fft.jit_probe(24000)
+    monkeypatch.setenv("B200FFT_ROWS_INPLACE", "0")            # A/B knob, read per plan
+    assert kernel(2187).startswith("jitrows2187_27x9x9_c3_")
+    with pytest.raises(b200fft.B200FFTError):
+        b200fft.jit_probe(20000)
+
+
 def test_jit_disk_cache(tmp_path):
     """A kernel compiled by one process is loaded from the on-disk cache by the next (fresh processes: the cache
     directory is read once per process); a rebuilt library (different header text) or another key never matches."""
