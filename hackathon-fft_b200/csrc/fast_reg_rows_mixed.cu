@@ -17,8 +17,8 @@ void register_rows_mixed() {
   reg_rows<640, 8, 256, true, 32, 20>();
   // contiguous axes of the reference's 1080p / 4K / 8K shapes (bench.mojo:112-115)
   reg_rows<1080, 4, 144, true, 36, 30>();
-  // complex input: one shared buffer, the middle stage exchanged in place (rows_ip_kernel; profiles/r2_long_rows.md:
-  // 12000 x 2160 0.107 -> 0.075 ms, 6000 x 4320 0.104 -> 0.076); the two-buffer kernels serve real input and R2C / C2R
+  // complex or real input, full spectrum: one shared buffer, the middle stage exchanged in place (rows_ip_kernel; profiles/r2_long_rows.md:
+  // 12000 x 2160 0.107 -> 0.075 ms, 6000 x 4320 0.104 -> 0.076); the two-buffer kernels serve R2C / C2R
   reg_rows_inplace<2160, 144, 16, 15, 9>();
   reg_rows_inplace<4320, 288, 16, 18, 15>();
   reg_rows<2160, 2, 288, true, 16, 15, 9>();

@@ -26,10 +26,10 @@ void register_rows_pow2() {
   reg_rows<1024, 8, 256, true, 32, 32>();
   reg_rows_v4<1024, 8, 256, true, 32, 32>();
   reg_rows<1024, 4, 256, true, 16, 16, 4>();
-  reg_rows_inplace<2048, 128, 16, 16, 8>();    // complex input: 17 KB per row (12800 x 2048: 0.100 -> 0.070 ms)
+  reg_rows_inplace<2048, 128, 16, 16, 8>();    // 17 KB per row (12800 x 2048: 0.100 -> 0.070 ms)
   reg_rows<2048, 4, 256, true, 32, 8, 8>();
-  reg_rows_inplace<4096, 256, 16, 16, 16>();   // complex input: 35 KB per row, six CTAs per SM (25000 x 4096: 0.50 -> 0.26 ms)
-  reg_rows<4096, 2, 256, true, 16, 16, 16>();  // real input, and the H-point core of 8192-point R2C / C2R
+  reg_rows_inplace<4096, 256, 16, 16, 16>();   // 35 KB per row, six CTAs per SM (25000 x 4096: 0.50 -> 0.26 ms)
+  reg_rows<4096, 2, 256, true, 16, 16, 16>();  // the H-point core of 8192-point R2C / C2R
   reg_rows_inplace<16384, 512, 32, 32, 16>();  // (100, 16384), fft/bench.mojo:111: one launch instead of two split passes
   reg_rows_inplace<8192, 256, 32, 16, 16>();
 }

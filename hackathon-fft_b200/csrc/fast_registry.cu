@@ -311,7 +311,7 @@ std::unique_ptr<Pass> make_fast_pass(b200fft_plan& plan, int axis, const AxisVie
     const bool ip_ok = !(ip_env && ip_env[0] == '0');
     for (const Variant& v : registry()) {
       const bool kind_ok = (v.kind == kind || (v.kind == COLS_TMA && tma_ok)) && (ip_ok || !v.inv_ok);
-      if (kind_ok && v.n == (int)view.n && (v.full || (src.comps == 2 && (!p.desc.inverse || v.inv_ok))) &&
+      if (kind_ok && v.n == (int)view.n && (v.full || v.inv_ok || (!p.desc.inverse && src.comps == 2)) &&
           can_group(ax.ordered, v.radices))
         cands.push_back(&v);
     }

@@ -29,7 +29,7 @@ struct Variant {
   int box_rows = 0;  // TMA box extent along the transform axis
   void (*launch_scatter)(bool, const ColsArgs&, const ScatterArgs&, unsigned, size_t, cudaStream_t) = nullptr;
   bool full;  // has inverse and real-input instantiations
-  bool inv_ok = false;  // not FULL, but complex inverse exists too (long in-place rows)
+  bool inv_ok = false;  // not FULL (no R2C / C2R forms), but inverse and real-input instantiations exist (one-buffer rows)
   // half-spectrum real transforms of length 2*n on top of this n-point row variant (FULL only)
   void (*launch_half)(bool c2r, const HalfArgs&, unsigned, cudaStream_t) = nullptr;
   cudaError_t (*prepare_half)() = nullptr;
@@ -109,14 +109,18 @@ struct RowsV {
 
 template <int N, class RL, int NT>
 struct RowsIpV {
-  static void launch(bool inv, bool, const RowsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
-    if (inv) rows_ip_kernel<N, RL, 1, NT, true><<<grid, NT, smem, st>>>(a);
-    else rows_ip_kernel<N, RL, 1, NT, false><<<grid, NT, smem, st>>>(a);
+  static void launch(bool inv, bool real, const RowsArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+    if (inv && real) rows_ip_kernel<N, RL, 1, NT, true, true><<<grid, NT, smem, st>>>(a);
+    else if (inv) rows_ip_kernel<N, RL, 1, NT, true, false><<<grid, NT, smem, st>>>(a);
+    else if (real) rows_ip_kernel<N, RL, 1, NT, false, true><<<grid, NT, smem, st>>>(a);
+    else rows_ip_kernel<N, RL, 1, NT, false, false><<<grid, NT, smem, st>>>(a);
   }
   static cudaError_t prepare(size_t smem) {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    cudaError_t e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, 1, NT, false>, attr, (int)smem);
-    if (!e) e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, 1, NT, true>, attr, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, 1, NT, false, false>, attr, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, 1, NT, true, false>, attr, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, 1, NT, false, true>, attr, (int)smem);
+    if (!e) e = cudaFuncSetAttribute(rows_ip_kernel<N, RL, 1, NT, true, true>, attr, (int)smem);
     return e;
   }
 };
@@ -266,7 +270,7 @@ template <int N, int C, int NT, bool FULL, int... Rs>
 void reg_rows_v4() {
   reg_rows_impl<N, C, NT, FULL, true, Rs...>();
 }
-// one long row per CTA, three stages in one shared buffer (rows_ip_kernel): complex input, forward and inverse
+// one long row per CTA, three stages in one shared buffer (rows_ip_kernel): complex or real input, forward and inverse
 template <int N, int NT, int... Rs>
 void reg_rows_inplace() {
   using RL = Radices<Rs...>;

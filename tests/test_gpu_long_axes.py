@@ -75,11 +75,11 @@ def test_split_respects_user_bases():
     assert "split n=1920 = 128 x 15" in desc and rel < 2e-6, desc
 
 
-@pytest.mark.parametrize("n", [2048, 2160, 4096, 4320, 8192])
+@pytest.mark.parametrize("n", [2048, 2160, 4096, 4320, 8192, 16384])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_registered_one_buffer_rows(n, inverse):
-    """The registered one-buffer variants (fast_reg_rows_*.cu: reg_rows_inplace) serve complex input in both directions;
-    real input of the same lengths stays on the two-buffer variants."""
+    """The registered one-buffer variants (fast_reg_rows_*.cu: reg_rows_inplace) serve complex and real input (full
+    spectrum out) in both directions; R2C / C2R of these lengths stay on the two-buffer variants."""
     rel, mx, desc = _run((301, n), inverse)
     assert "rowsIP%d_" % n in desc and desc.strip().count("\n") == 0, desc
     assert rel < 2e-6 and mx < 1e-5, (rel, mx)
@@ -87,7 +87,7 @@ def test_registered_one_buffer_rows(n, inverse):
     x = torch.randn(5, n, 1, device="cuda")
     out = torch.empty(5, n, 2, device="cuda")
     plan = b200fft.plan_fft("float32", "float32", x.shape, out.shape)
-    assert "generic" not in plan.describe(), plan.describe()
+    assert "rowsIP%d_" % n in plan.describe() and "real-in" in plan.describe(), plan.describe()
     b200fft.fft(out, x, plan=plan)
     torch.cuda.synchronize()
     plan.destroy()
