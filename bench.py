@@ -65,6 +65,10 @@ SHAPES = [
     # counterpart of the reference specialising every shape at compile time (profiles/r2_jit_tier.md)
     ("1d_50000x1000_plan_time_specialised", (50000, 1000), False),
     ("3d_4x200x200x200_plan_time_specialised", (4, 200, 200, 200), False),
+    # long contiguous rows: one launch, one shared exchange buffer (rows_ip_kernel; profiles/r2_long_rows.md). (100, 16384)
+    # is the reference's published shape (fft/bench.mojo:111)
+    ("1d_100x16384", (100, 16384), False),
+    ("1d_25000x4096", (25000, 4096), False),
 ]
 
 
